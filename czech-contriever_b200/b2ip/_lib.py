@@ -1,0 +1,94 @@
+"""ctypes binding of libb2ip.so (C ABI: include/b2ip.h).
+
+There is deliberately no fallback: if the shared library is missing or no B200 is visible the
+import of the library / creation of an engine raises, it never degrades to a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libb2ip.so")
+
+B2IP_OK = 0
+B2IP_F32, B2IP_F16 = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+MODE_AUTO, MODE_TENSOR, MODE_EXACT = 0, 1, 2
+MAX_K = 2048
+
+# every symbol include/b2ip.h declares (tests check the .so exports all of them)
+SYMBOLS = (
+    "b2ip_create", "b2ip_destroy", "b2ip_set_stream", "b2ip_reserve", "b2ip_add", "b2ip_ntotal",
+    "b2ip_dim", "b2ip_set_row_offset", "b2ip_search", "b2ip_merge_topk", "b2ip_export_rows",
+    "b2ip_stats", "b2ip_last_error", "b2ip_debug_coarse_scores", "b2ip_version",
+)
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("nq", ctypes.c_int64), ("ntotal", ctypes.c_int64),
+        ("k", ctypes.c_int32), ("mode_used", ctypes.c_int32),
+        ("coarse_launches", ctypes.c_int32), ("total_launches", ctypes.c_int32),
+        ("coarse_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+        ("coarse_flops", ctypes.c_double),
+        ("candidates", ctypes.c_int64), ("rescored", ctypes.c_int64),
+        ("fallback_queries", ctypes.c_int64),
+        ("slabs", ctypes.c_int32), ("query_batches", ctypes.c_int32),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class B2ipError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb2ip error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen libb2ip.so and declare the prototypes.  Raises if it has not been built
+    (`python -c "import __graft_entry__ as g; g.build()"` or `make -C czech-contriever_b200/csrc`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA library first "
+            "(make -C czech-contriever_b200/csrc). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.b2ip_create.argtypes = [i32, i32, ctypes.POINTER(vp)]
+    lib.b2ip_destroy.argtypes = [vp]
+    lib.b2ip_destroy.restype = None
+    lib.b2ip_set_stream.argtypes = [vp, vp]
+    lib.b2ip_reserve.argtypes = [vp, i64]
+    lib.b2ip_add.argtypes = [vp, i64, vp, i32, i32]
+    lib.b2ip_ntotal.argtypes = [vp]
+    lib.b2ip_ntotal.restype = i64
+    lib.b2ip_dim.argtypes = [vp]
+    lib.b2ip_set_row_offset.argtypes = [vp, i64]
+    lib.b2ip_search.argtypes = [vp, i64, vp, i32, vp, vp, i32, i32]
+    lib.b2ip_merge_topk.argtypes = [i32, vp, i64, i32, i32, vp, vp, vp, vp]
+    lib.b2ip_export_rows.argtypes = [vp, i64, i64, vp, i32]
+    lib.b2ip_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    lib.b2ip_last_error.argtypes = [vp]
+    lib.b2ip_last_error.restype = ctypes.c_char_p
+    lib.b2ip_debug_coarse_scores.argtypes = [vp, i64, vp, i64, i64, vp]
+    lib.b2ip_version.restype = ctypes.c_char_p
+    for name in ("b2ip_create", "b2ip_set_stream", "b2ip_reserve", "b2ip_add", "b2ip_dim",
+                 "b2ip_set_row_offset", "b2ip_search", "b2ip_merge_topk", "b2ip_export_rows",
+                 "b2ip_stats", "b2ip_debug_coarse_scores"):
+        getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc: int, handle=None) -> None:
+    if rc != B2IP_OK:
+        msg = load().b2ip_last_error(handle)
+        raise B2ipError(rc, msg.decode() if msg else "")

@@ -1,0 +1,164 @@
+"""`Engine`: one row shard of the exact IP index on one B200, over the C ABI.
+
+Accepts numpy arrays (host buffers) or torch CUDA tensors (device buffers, zero copy); torch is
+only imported when a tensor is handed in.  Mirrors what the reference does with its faiss
+object in src/index.py: `add` <- index.add (:30), `search` <- index.search (:42),
+`ntotal` <- index.ntotal (:67), `export_rows` <- what faiss.write_index reads (:53).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import (B2IP_F16, B2IP_F32, MEM_DEVICE, MEM_HOST, MODE_AUTO, MODE_EXACT, MODE_TENSOR,
+                   B2ipError, Stats, check)
+
+_MODES = {"auto": MODE_AUTO, "tensor": MODE_TENSOR, "exact": MODE_EXACT}
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class Engine:
+    def __init__(self, d: int, device: int = 0):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        check(self._lib.b2ip_create(int(d), int(device), ctypes.byref(self._h)), None)
+        self.d = int(d)
+        self.device = int(device)
+
+    # -- lifetime ------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.b2ip_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration -------------------------------------------------------------
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        """Run on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(self._lib.b2ip_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)), self._h)
+
+    def use_torch_stream(self) -> None:
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reserve(self, n_rows: int) -> None:
+        check(self._lib.b2ip_reserve(self._h, int(n_rows)), self._h)
+
+    def set_row_offset(self, offset: int) -> None:
+        check(self._lib.b2ip_set_row_offset(self._h, int(offset)), self._h)
+
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.b2ip_ntotal(self._h))
+
+    # -- data ----------------------------------------------------------------------
+    def add(self, rows) -> None:
+        """Append rows [n,d]; float16 is widened exactly, anything else goes through float32
+        (reference: `embeddings.astype('float32')`, src/index.py:27)."""
+        if _is_torch(rows):
+            import torch
+            assert rows.is_cuda and rows.device.index == self.device, "tensor must live on the engine's GPU"
+            if rows.dtype not in (torch.float16, torch.float32):
+                rows = rows.float()
+            rows = rows.contiguous()
+            assert rows.dim() == 2 and rows.shape[1] == self.d, tuple(rows.shape)
+            torch.cuda.current_stream(self.device).synchronize()
+            dt = B2IP_F16 if rows.dtype == torch.float16 else B2IP_F32
+            check(self._lib.b2ip_add(self._h, rows.shape[0], ctypes.c_void_p(rows.data_ptr()), dt,
+                                     MEM_DEVICE), self._h)
+            return
+        rows = np.asarray(rows)
+        if rows.dtype not in (np.float16, np.float32):
+            rows = rows.astype(np.float32)
+        rows = np.ascontiguousarray(rows)
+        if rows.ndim != 2 or rows.shape[1] != self.d:
+            raise ValueError(f"expected [n,{self.d}] rows, got {rows.shape}")
+        dt = B2IP_F16 if rows.dtype == np.float16 else B2IP_F32
+        check(self._lib.b2ip_add(self._h, rows.shape[0], ctypes.c_void_p(rows.ctypes.data), dt,
+                                 MEM_HOST), self._h)
+
+    def export_rows(self, row0: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.d), dtype=np.float32)
+        check(self._lib.b2ip_export_rows(self._h, int(row0), int(n), ctypes.c_void_p(out.ctypes.data),
+                                         MEM_HOST), self._h)
+        return out
+
+    # -- search --------------------------------------------------------------------
+    def search(self, queries, k: int, mode: str = "auto", out=None) -> Tuple[object, object]:
+        """(scores [nq,k] float32 descending, rows [nq,k] int64).  numpy in -> numpy out (host
+        buffers cross the ABI, H2D/D2H inside the call); torch CUDA tensor in -> tensors out."""
+        m = _MODES[mode]
+        k = int(k)
+        if _is_torch(queries):
+            import torch
+            assert queries.is_cuda and queries.device.index == self.device
+            q = queries.float().contiguous()
+            assert q.dim() == 2 and q.shape[1] == self.d, tuple(q.shape)
+            nq = q.shape[0]
+            if out is None:
+                D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+                I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            else:
+                D, I = out
+            torch.cuda.current_stream(self.device).synchronize()
+            check(self._lib.b2ip_search(self._h, nq, ctypes.c_void_p(q.data_ptr()), k,
+                                        ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                        m, MEM_DEVICE), self._h)
+            return D, I
+        q = np.ascontiguousarray(np.asarray(queries), dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.d:
+            raise ValueError(f"expected [nq,{self.d}] queries, got {q.shape}")
+        nq = q.shape[0]
+        if out is None:
+            D = np.empty((nq, k), dtype=np.float32)
+            I = np.empty((nq, k), dtype=np.int64)
+        else:
+            D, I = out
+        check(self._lib.b2ip_search(self._h, nq, ctypes.c_void_p(q.ctypes.data), k,
+                                    ctypes.c_void_p(D.ctypes.data), ctypes.c_void_p(I.ctypes.data),
+                                    m, MEM_HOST), self._h)
+        return D, I
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(self._lib.b2ip_stats(self._h, ctypes.byref(s)), self._h)
+        return s.as_dict()
+
+    def debug_coarse_scores(self, queries, row0: int, n_rows: int):
+        """Test hook: raw tcgen05 bf16 scores [nq,n_rows] (torch CUDA tensors only)."""
+        import torch
+        q = queries.float().contiguous()
+        out = torch.empty((q.shape[0], n_rows), dtype=torch.float32, device=q.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        check(self._lib.b2ip_debug_coarse_scores(self._h, q.shape[0], ctypes.c_void_p(q.data_ptr()),
+                                                 int(row0), int(n_rows), ctypes.c_void_p(out.data_ptr())),
+              self._h)
+        return out
+
+
+def merge_topk(scores, rows, k: int):
+    """Device merge of per-shard results: scores/rows torch CUDA tensors [G,nq,k] -> ([nq,k],[nq,k])."""
+    import torch
+    lib = _lib.load()
+    G, nq, kk = scores.shape
+    assert kk == k and rows.shape == scores.shape
+    scores = scores.contiguous()
+    rows = rows.contiguous()
+    D = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
+    stream = torch.cuda.current_stream(scores.device)
+    check(lib.b2ip_merge_topk(scores.device.index, ctypes.c_void_p(stream.cuda_stream), nq, k, G,
+                              ctypes.c_void_p(scores.data_ptr()), ctypes.c_void_p(rows.data_ptr()),
+                              ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr())), None)
+    return D, I

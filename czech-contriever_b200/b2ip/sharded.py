@@ -1,0 +1,117 @@
+"""Row-sharded search across the GPUs of one box: one process per GPU (`torchrun`), each rank
+owns a set of corpus segments in its own `Engine`, queries are replicated, every rank computes
+a local top-k and the one exchange step is an all-gather of the [nq,k] (score, global row)
+blocks over NCCL/NVLink followed by the merge kernel.
+
+The reference runs this path in a single process on host cores (faiss OpenMP,
+src/index.py:42); sharding is how the same search is spread over 1/2/4/8 B200s.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+
+def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row shard of `rank`: [rank*ceil(N/G), min((rank+1)*ceil(N/G), N))."""
+    per = -(-n_total // world) if world > 0 else n_total
+    lo = min(rank * per, n_total)
+    return lo, min(lo + per, n_total)
+
+
+class ShardedIndex:
+    def __init__(self, d: int, device: Optional[int] = None, engine=None, group=None,
+                 merge_fn: Optional[Callable] = None):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist = torch, dist
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        if engine is None:
+            from .engine import Engine, merge_topk
+            if device is None:
+                device = torch.cuda.current_device()
+            engine = Engine(d, device)
+            merge_fn = merge_fn or merge_topk
+        self.engine = engine
+        self.merge_fn = merge_fn
+        self.d = d
+        self.segments: List[Tuple[int, int, int]] = []   # (local_start, global_start, n)
+        self._n_local = 0
+        self._n_seen = 0          # add_replicated: rows seen by every rank so far
+        self._chunk_no = 0
+        self._seg_cache = None
+
+    # -- ingest ----------------------------------------------------------------------
+    def add_local(self, rows, global_start: int) -> None:
+        """Rows this rank owns; they take global ids global_start .. global_start+n-1.
+        Segments must be added in increasing global order (keeps the lower-row tie rule)."""
+        n = int(rows.shape[0])
+        if n == 0:
+            return
+        if self.segments and global_start < self.segments[-1][1] + self.segments[-1][2]:
+            raise ValueError("segments must be appended in increasing global row order")
+        self.engine.add(rows)
+        if self.segments and self.segments[-1][1] + self.segments[-1][2] == global_start:
+            ls, gs, m = self.segments[-1]
+            self.segments[-1] = (ls, gs, m + n)
+        else:
+            self.segments.append((self._n_local, int(global_start), n))
+        self._n_local += n
+        self._seg_cache = None
+
+    def add_replicated(self, rows) -> None:
+        """SPMD ingest: every rank is handed the SAME chunk (the reference's `index_data`
+        stream, passage_retrieval.py:65-91); chunk i is kept by rank i % world."""
+        n = int(rows.shape[0])
+        if self._chunk_no % self.world == self.rank:
+            self.add_local(rows, self._n_seen)
+        self._n_seen += n
+        self._chunk_no += 1
+
+    @property
+    def ntotal_local(self) -> int:
+        return self._n_local
+
+    # -- search ----------------------------------------------------------------------
+    def _to_global(self, rows_local):
+        torch = self._torch
+        if not self.segments:
+            return rows_local
+        if len(self.segments) == 1:
+            ls, gs, _ = self.segments[0]
+            return torch.where(rows_local >= 0, rows_local + (gs - ls), rows_local)
+        if self._seg_cache is None or self._seg_cache[0].device != rows_local.device:
+            ls = torch.tensor([s[0] for s in self.segments], dtype=torch.int64, device=rows_local.device)
+            delta = torch.tensor([s[1] - s[0] for s in self.segments], dtype=torch.int64,
+                                 device=rows_local.device)
+            self._seg_cache = (ls, delta)
+        ls, delta = self._seg_cache
+        seg = torch.bucketize(rows_local.clamp(min=0), ls, right=True) - 1
+        return torch.where(rows_local >= 0, rows_local + delta[seg], rows_local)
+
+    def search_local(self, queries, k: int, mode: str = "auto"):
+        D, I = self.engine.search(queries, k, mode=mode)
+        return D, self._to_global(I)
+
+    def search(self, queries, k: int, mode: str = "auto"):
+        """queries: [nq,d] tensor on this rank's device (identical on all ranks).
+        Returns the global (scores [nq,k], rows [nq,k]) on every rank."""
+        torch, dist = self._torch, self._dist
+        D, I = self.search_local(queries, k, mode)
+        if self.world == 1:
+            return D, I
+        gD = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+        gI = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+        try:
+            dist.all_gather_into_tensor(gD, D.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(gI, I.contiguous(), group=self.group)
+        except (RuntimeError, NotImplementedError):
+            lD = [torch.empty_like(D) for _ in range(self.world)]
+            lI = [torch.empty_like(I) for _ in range(self.world)]
+            dist.all_gather(lD, D.contiguous(), group=self.group)
+            dist.all_gather(lI, I.contiguous(), group=self.group)
+            gD, gI = torch.stack(lD), torch.stack(lI)
+        return self.merge_fn(gD, gI, k)

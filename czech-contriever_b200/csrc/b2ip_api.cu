@@ -1,0 +1,657 @@
+// b2ip_api.cu -- host side of libb2ip.so: index state in HBM, slab scheduling of the
+// tensor path, the exact fallback, and the C ABI declared in include/b2ip.h.
+//
+// HBM layout of one index (= one row shard on one GPU):
+//   x32 [n, d]      fp32 master rows   (rescore, export, exact path)   -- what faiss keeps on host
+//   x16 [n, d_pad]  bf16 shadow rows   (operand of the tcgen05 coarse GEMM), d_pad = ceil64(d)
+//   norm_stats[2]   max ||x||^2, max ||x - bf16(x)||^2 (error bound of the coarse scores)
+// Per search (grow-only workspace): bf16 queries, eps2/thr/cnt/kept/flags per query, candidate
+// lists [nq_batch, cap] of 64-bit keys, device outputs.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b2ip.h"
+#include "coarse_kernel.cuh"
+#include "select_kernels.cuh"
+
+using namespace b2ip;
+
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct b2ip_index_s {
+    int d = 0, d_pad = 0, device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    float* x32 = nullptr;
+    __nv_bfloat16* x16 = nullptr;
+    int64_t n = 0, cap_rows = 0, row_offset = 0;
+    unsigned int* norm_stats = nullptr;   // device [2]
+    long long* gstats = nullptr;          // device [GS_COUNT]
+    long long* h_gstats = nullptr;        // pinned host mirror
+    PFN_encodeTiled encode = nullptr;
+    // grow-only workspace
+    DevBuf q16, eps2, thr, cnt, kept, flags, cand, qstage, out_s, out_r, exact_scores, exact_misc,
+        qlist, stage;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    b2ip_stats_t stats;
+    std::string err;
+    int gx = 32;
+    long long cand_budget_bytes = 6ll << 30;
+};
+
+namespace {
+
+int fail(b2ip_handle h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU_TRY(h, expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            cudaGetLastError();                                                               \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? B2IP_ERR_OOM : B2IP_ERR_CUDA,   \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,    \
+                        __LINE__);                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define RC_TRY(expr)                 \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != B2IP_OK) return rc__; \
+    } while (0)
+
+int ensure(b2ip_handle h, DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes) return B2IP_OK;
+    if (b.p) { CU_TRY(h, cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMalloc(&b.p, want); }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.p = nullptr;
+        return fail(h, B2IP_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.bytes = want;
+    return B2IP_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+int grow_rows(b2ip_handle h, int64_t need, bool exact = false) {
+    if (need <= h->cap_rows) return B2IP_OK;
+    int64_t ncap = need;
+    if (!exact) ncap = std::max<int64_t>(std::max<int64_t>(need, h->cap_rows + h->cap_rows / 2), 4096);
+    float* nx32 = nullptr;
+    __nv_bfloat16* nx16 = nullptr;
+    cudaError_t e = cudaMalloc(&nx32, static_cast<size_t>(ncap) * h->d * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&nx16, static_cast<size_t>(ncap) * h->d_pad * 2);
+    if (e != cudaSuccess && ncap > need) {   // retry with the exact size
+        cudaGetLastError();
+        if (nx32) cudaFree(nx32);
+        nx32 = nullptr; nx16 = nullptr;
+        ncap = need;
+        e = cudaMalloc(&nx32, static_cast<size_t>(ncap) * h->d * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&nx16, static_cast<size_t>(ncap) * h->d_pad * 2);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (nx32) cudaFree(nx32);
+        if (nx16) cudaFree(nx16);
+        return fail(h, B2IP_ERR_OOM, "growing the index to %lld rows failed: %s",
+                    static_cast<long long>(ncap), cudaGetErrorString(e));
+    }
+    if (h->n > 0) {
+        CU_TRY(h, cudaMemcpyAsync(nx32, h->x32, static_cast<size_t>(h->n) * h->d * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(nx16, h->x16, static_cast<size_t>(h->n) * h->d_pad * 2,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    if (h->x32) cudaFree(h->x32);
+    if (h->x16) cudaFree(h->x16);
+    h->x32 = nx32;
+    h->x16 = nx16;
+    h->cap_rows = ncap;
+    return B2IP_OK;
+}
+
+int make_tmap_bf16(b2ip_handle h, CUtensorMap* m, const void* base, int64_t rows, int d_pad,
+                   int box_rows) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_pad) * 2};
+    cuuint32_t box[2] = {KBLOCK_ELEMS, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, B2IP_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d, rows=%lld d_pad=%d)",
+                    static_cast<int>(r), static_cast<long long>(rows), d_pad);
+    return B2IP_OK;
+}
+
+cudaEvent_t get_event(b2ip_handle h, size_t i) {
+    while (h->ev_pool.size() <= i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev_pool.push_back(e);
+    }
+    return h->ev_pool[i];
+}
+
+struct Guard {   // selects the index's device for the duration of a call
+    int prev = -1;
+    explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------- exact path
+// Scores qlist's queries (indices into q32) against the whole shard in fp32 and writes their
+// top-k.  qlist_dev == nullptr means queries [q_begin, q_begin + nql).
+int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t nql, int k,
+                 float* d_scores, int64_t* d_rows) {
+    const int64_t n = h->n;
+    RC_TRY(ensure(h, h->exact_scores, static_cast<size_t>(EXACT_QB) * n * sizeof(float)));
+    const size_t misc_bytes = sizeof(ExactState) + EXACT_QB * 256 * sizeof(unsigned int) +
+                              EXACT_QB * sizeof(int) + 64;
+    RC_TRY(ensure(h, h->exact_misc, misc_bytes));
+    RC_TRY(ensure(h, h->qlist, static_cast<size_t>(nql) * sizeof(int)));
+    const int cap = k;
+    RC_TRY(ensure(h, h->cand, static_cast<size_t>(EXACT_QB) * cap * sizeof(unsigned long long)));
+    auto* st = reinterpret_cast<ExactState*>(h->exact_misc.p);
+    auto* ghist = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(h->exact_misc.p) + sizeof(ExactState));
+    int* gcnt = reinterpret_cast<int*>(ghist + EXACT_QB * 256);
+    int* qlist_dev = reinterpret_cast<int*>(h->qlist.p);
+    CU_TRY(h, cudaMemcpyAsync(qlist_dev, qlist_host, static_cast<size_t>(nql) * sizeof(int),
+                              cudaMemcpyHostToDevice, h->stream));
+    const size_t sq_bytes = static_cast<size_t>(EXACT_QB) * h->d * sizeof(float);
+    CU_TRY(h, cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(sq_bytes)));
+    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
+    CU_TRY(h, cudaFuncSetAttribute(finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(fin_smem)));
+    const int sgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
+    const int hgrid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(h->sm_count) * 4));
+    for (int64_t g0 = 0; g0 < nql; g0 += EXACT_QB) {
+        const int nqg = static_cast<int>(std::min<int64_t>(EXACT_QB, nql - g0));
+        exact_scores_kernel<<<std::max(sgrid, 1), 256, sq_bytes, h->stream>>>(
+            h->x32, n, h->d, q32, qlist_dev + g0, nqg, reinterpret_cast<float*>(h->exact_scores.p));
+        exact_init_kernel<<<1, 256, 0, h->stream>>>(st, ghist, gcnt, k);
+        for (int pass = 0; pass < 8; pass++) {
+            exact_hist_kernel<<<dim3(std::max(hgrid, 1), nqg), 256, 0, h->stream>>>(
+                reinterpret_cast<float*>(h->exact_scores.p), n, pass, st, ghist);
+            exact_pick_kernel<<<nqg, 32, 0, h->stream>>>(st, ghist, pass);
+        }
+        exact_collect_kernel<<<dim3(std::max(hgrid, 1), nqg), 256, 0, h->stream>>>(
+            reinterpret_cast<float*>(h->exact_scores.p), n, st,
+            reinterpret_cast<unsigned long long*>(h->cand.p), gcnt, cap);
+        FinalizeParams fp{};
+        fp.k = k; fp.cap = cap; fp.d = h->d;
+        fp.qlist = qlist_dev + g0;
+        fp.cand = reinterpret_cast<unsigned long long*>(h->cand.p);
+        fp.cnt = gcnt; fp.flags = nullptr; fp.q32 = q32; fp.x32 = h->x32;
+        fp.row_offset = h->row_offset;
+        fp.out_scores = d_scores; fp.out_rows = reinterpret_cast<long long*>(d_rows);
+        fp.gstats = nullptr;
+        finalize_kernel<false><<<nqg, SEL_THREADS, fin_smem, h->stream>>>(fp);
+        h->stats.total_launches += 20;
+    }
+    CU_TRY(h, cudaGetLastError());
+    return B2IP_OK;
+}
+
+// ------------------------------------------------------------------------- tensor path
+int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_scores,
+                  int64_t* d_rows) {
+    const int64_t n = h->n;
+    const int cap = std::max(4096, 16 * k);
+    int64_t qb_max = h->cand_budget_bytes / (static_cast<int64_t>(cap) * 8);
+    qb_max = std::max<int64_t>(TILE_Q, qb_max / TILE_Q * TILE_Q);
+    const int64_t qb = std::min<int64_t>(nq, qb_max);
+
+    RC_TRY(ensure(h, h->q16, static_cast<size_t>(qb) * h->d_pad * 2));
+    RC_TRY(ensure(h, h->eps2, qb * sizeof(float)));
+    RC_TRY(ensure(h, h->thr, qb * sizeof(float)));
+    RC_TRY(ensure(h, h->cnt, qb * sizeof(int)));
+    RC_TRY(ensure(h, h->kept, qb * sizeof(int)));
+    RC_TRY(ensure(h, h->flags, qb * sizeof(int)));
+    RC_TRY(ensure(h, h->cand, static_cast<size_t>(qb) * cap * 8));
+
+    CU_TRY(h, cudaFuncSetAttribute(coarse_filter_kernel<false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES));
+    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
+    CU_TRY(h, cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(fin_smem)));
+
+    CUtensorMap tmap_x;
+    RC_TRY(make_tmap_bf16(h, &tmap_x, h->x16, n, h->d_pad, TILE_X));
+
+    size_t ev_used = 0;
+    std::vector<int> fallback;
+    for (int64_t q0 = 0; q0 < nq; q0 += qb) {
+        const int nqb = static_cast<int>(std::min<int64_t>(qb, nq - q0));
+        h->stats.query_batches++;
+        const float* qptr = q32 + q0 * h->d;
+        CU_TRY(h, cudaMemsetAsync(h->gstats, 0, GS_COUNT * sizeof(long long), h->stream));
+        prep_queries_kernel<<<(nqb + 7) / 8, 256, 0, h->stream>>>(
+            qptr, reinterpret_cast<__nv_bfloat16*>(h->q16.p), nqb, h->d, h->d_pad, h->norm_stats,
+            reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
+            reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p),
+            reinterpret_cast<int*>(h->flags.p));
+        h->stats.total_launches++;
+        CUtensorMap tmap_q;
+        RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, nqb, h->d_pad, TILE_Q));
+
+        CoarseParams cp{};
+        cp.num_k_blocks = h->d_pad / KBLOCK_ELEMS;
+        cp.q_tiles = (nqb + TILE_Q - 1) / TILE_Q;
+        cp.gx = h->gx;
+        cp.nq = nqb;
+        cp.thr = reinterpret_cast<float*>(h->thr.p);
+        cp.cand = reinterpret_cast<unsigned long long*>(h->cand.p);
+        cp.cnt = reinterpret_cast<int*>(h->cnt.p);
+        cp.cap = cap;
+        cp.dump = nullptr;
+        cp.dump_ld = 0;
+
+        int64_t done = 0;
+        int64_t slab = std::min<int64_t>(cap, std::max<int64_t>(1024, 8ll * k));
+        slab = slab / TILE_X * TILE_X;
+        long long overflowed = 0;
+        while (done < n) {
+            int64_t s = std::min<int64_t>(slab, n - done);
+            if (done + s < n) s = std::max<int64_t>(TILE_X, s / TILE_X * TILE_X);
+            s = std::min<int64_t>(s, n - done);
+            cp.x_row0 = done;
+            cp.x_row_end = done + s;
+            cp.x_tiles = static_cast<int>((s + TILE_X - 1) / TILE_X);
+            const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
+            const int grid = static_cast<int>(std::min<long long>(tiles, h->sm_count));
+            cudaEvent_t e0 = get_event(h, ev_used++), e1 = get_event(h, ev_used++);
+            CU_TRY(h, cudaEventRecord(e0, h->stream));
+            coarse_filter_kernel<false><<<grid, COARSE_THREADS, COARSE_SMEM_BYTES, h->stream>>>(
+                tmap_q, tmap_x, cp);
+            CU_TRY(h, cudaEventRecord(e1, h->stream));
+            refresh_threshold_kernel<<<nqb, SEL_THREADS, 0, h->stream>>>(
+                k, cap, cp.cand, cp.cnt, reinterpret_cast<int*>(h->kept.p),
+                reinterpret_cast<float*>(h->thr.p), reinterpret_cast<float*>(h->eps2.p),
+                reinterpret_cast<int*>(h->flags.p), h->gstats);
+            CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
+                                      cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            CU_TRY(h, cudaGetLastError());
+            h->stats.coarse_launches++;
+            h->stats.total_launches += 2;
+            h->stats.slabs++;
+            h->stats.coarse_flops += 2.0 * nqb * static_cast<double>(s) * h->d;
+            done += s;
+            const long long m_max = std::max<long long>(h->h_gstats[GS_MAX_KEPT], 1);
+            overflowed = h->h_gstats[GS_OVERFLOW];
+            // next slab: expected new hits per query ~ m_max * slab / done; keep the list
+            // below ~70 % of its capacity so Poisson noise does not overflow it.
+            const double room = 0.70 * cap - static_cast<double>(m_max);
+            double next = room > 0 ? static_cast<double>(done) * room / static_cast<double>(m_max)
+                                   : static_cast<double>(TILE_X);
+            next = std::min(next, 4.0e9);
+            slab = std::max<int64_t>(TILE_X, static_cast<int64_t>(next));
+        }
+        h->stats.candidates += h->h_gstats[GS_CANDIDATES];
+
+        FinalizeParams fp{};
+        fp.k = k; fp.cap = cap; fp.d = h->d;
+        fp.qlist = nullptr;
+        fp.cand = cp.cand;
+        fp.cnt = reinterpret_cast<int*>(h->kept.p);
+        fp.flags = reinterpret_cast<int*>(h->flags.p);
+        fp.q32 = qptr; fp.x32 = h->x32;
+        fp.row_offset = h->row_offset;
+        fp.out_scores = d_scores + q0 * k;
+        fp.out_rows = reinterpret_cast<long long*>(d_rows) + q0 * k;
+        fp.gstats = h->gstats;
+        finalize_kernel<true><<<nqb, SEL_THREADS, fin_smem, h->stream>>>(fp);
+        h->stats.total_launches++;
+        CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
+                                  cudaMemcpyDeviceToHost, h->stream));
+        std::vector<int> hflags;
+        if (overflowed > 0) {
+            hflags.resize(nqb);
+            CU_TRY(h, cudaMemcpyAsync(hflags.data(), h->flags.p, nqb * sizeof(int),
+                                      cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        CU_TRY(h, cudaGetLastError());
+        h->stats.rescored += h->h_gstats[GS_RESCORED];
+        for (int i = 0; i < static_cast<int>(hflags.size()); i++)
+            if (hflags[i] & FLAG_OVERFLOW) fallback.push_back(static_cast<int>(q0 + i));
+    }
+    // scoring-kernel time from the recorded event pairs
+    float ms_sum = 0.f;
+    for (size_t i = 0; i + 1 < ev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]) == cudaSuccess) ms_sum += ms;
+    }
+    h->stats.coarse_ms = ms_sum;
+    if (!fallback.empty()) {
+        h->stats.fallback_queries = static_cast<int64_t>(fallback.size());
+        RC_TRY(exact_search(h, q32, fallback.data(), static_cast<int64_t>(fallback.size()), k,
+                            d_scores, d_rows));
+    }
+    return B2IP_OK;
+}
+
+int search_device(b2ip_handle h, int64_t nq, const float* dq, int k, float* d_scores,
+                  int64_t* d_rows, int mode) {
+    memset(&h->stats, 0, sizeof(h->stats));
+    h->stats.nq = nq; h->stats.ntotal = h->n; h->stats.k = k;
+    if (nq == 0) return B2IP_OK;
+    CU_TRY(h, cudaEventRecord(h->ev_t0, h->stream));
+    if (h->n == 0) {
+        fill_padding_kernel<<<256, 256, 0, h->stream>>>(d_scores, reinterpret_cast<long long*>(d_rows), nq * k);
+        h->stats.total_launches = 1;
+        h->stats.mode_used = B2IP_MODE_EXACT;
+    } else if (mode == B2IP_MODE_EXACT) {
+        h->stats.mode_used = B2IP_MODE_EXACT;
+        std::vector<int> all(nq);
+        for (int64_t i = 0; i < nq; i++) all[i] = static_cast<int>(i);
+        RC_TRY(exact_search(h, dq, all.data(), nq, k, d_scores, d_rows));
+    } else {
+        h->stats.mode_used = B2IP_MODE_TENSOR;
+        RC_TRY(tensor_search(h, dq, nq, k, d_scores, d_rows));
+    }
+    CU_TRY(h, cudaEventRecord(h->ev_t1, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
+    h->stats.total_ms = ms;
+    return B2IP_OK;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" {
+
+const char* b2ip_version(void) { return "b2ip 0.1 sm_100a (tcgen05 bf16 coarse + fp32 rescore)"; }
+
+int b2ip_create(int d, int device, b2ip_handle* out) {
+    if (!out) return fail(nullptr, B2IP_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (d <= 0 || d % 4 != 0 || d > 4096)
+        return fail(nullptr, B2IP_ERR_INVALID, "d=%d: dimension must be a multiple of 4 in [4,4096]", d);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, B2IP_ERR_CUDA,
+                    "no CUDA device (%s): libb2ip has no CPU fallback", cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, B2IP_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(nullptr, B2IP_ERR_CUDA, "cudaGetDeviceProperties(%d) failed", device);
+    if (prop.major != 10)
+        return fail(nullptr, B2IP_ERR_UNSUPPORTED,
+                    "device %d is sm_%d%d; libb2ip is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    b2ip_handle h = new b2ip_index_s();
+    h->d = d;
+    h->d_pad = (d + KBLOCK_ELEMS - 1) / KBLOCK_ELEMS * KBLOCK_ELEMS;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    Guard g(device);
+    auto bail = [&](int code, const char* what) {
+        std::string msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
+        b2ip_destroy(h);
+        return fail(nullptr, code, "%s", msg.c_str());
+    };
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(B2IP_ERR_CUDA, "cudaStreamCreate");
+    h->stream = h->own_stream;
+    if (cudaMalloc(&h->norm_stats, 2 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&h->gstats, GS_COUNT * sizeof(long long)) != cudaSuccess ||
+        cudaMallocHost(&h->h_gstats, GS_COUNT * sizeof(long long)) != cudaSuccess)
+        return bail(B2IP_ERR_OOM, "allocating index state");
+    cudaMemset(h->norm_stats, 0, 2 * sizeof(unsigned int));
+    cudaEventCreate(&h->ev_t0);
+    cudaEventCreate(&h->ev_t1);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn)
+        return bail(B2IP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    if (const char* s = getenv("B2IP_GX")) h->gx = std::max(1, atoi(s));
+    if (const char* s = getenv("B2IP_CAND_BUDGET_MB")) h->cand_budget_bytes = std::max(1ll, atoll(s)) << 20;
+    memset(&h->stats, 0, sizeof(h->stats));
+    *out = h;
+    return B2IP_OK;
+}
+
+void b2ip_destroy(b2ip_handle h) {
+    if (!h) return;
+    Guard g(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    for (DevBuf* b : {&h->q16, &h->eps2, &h->thr, &h->cnt, &h->kept, &h->flags, &h->cand, &h->qstage,
+                      &h->out_s, &h->out_r, &h->exact_scores, &h->exact_misc, &h->qlist, &h->stage})
+        release(*b);
+    if (h->x32) cudaFree(h->x32);
+    if (h->x16) cudaFree(h->x16);
+    if (h->norm_stats) cudaFree(h->norm_stats);
+    if (h->gstats) cudaFree(h->gstats);
+    if (h->h_gstats) cudaFreeHost(h->h_gstats);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int b2ip_set_stream(b2ip_handle h, void* cuda_stream) {
+    if (!h) return B2IP_ERR_INVALID;
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return B2IP_OK;
+}
+
+int b2ip_reserve(b2ip_handle h, int64_t n_rows) {
+    if (!h) return B2IP_ERR_INVALID;
+    if (n_rows < 0 || n_rows >= (1ll << 32)) return fail(h, B2IP_ERR_INVALID, "n_rows=%lld out of range", (long long)n_rows);
+    Guard g(h->device);
+    if (n_rows <= h->cap_rows) return B2IP_OK;
+    return grow_rows(h, n_rows, /*exact=*/true);   // a reserve states the final size
+}
+
+int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem) {
+    if (!h) return B2IP_ERR_INVALID;
+    if (n < 0 || (n > 0 && !rows)) return fail(h, B2IP_ERR_INVALID, "b2ip_add: bad rows pointer / n=%lld", (long long)n);
+    if (src_dtype != B2IP_F32 && src_dtype != B2IP_F16) return fail(h, B2IP_ERR_INVALID, "b2ip_add: src_dtype=%d", src_dtype);
+    if (mem != B2IP_MEM_HOST && mem != B2IP_MEM_DEVICE) return fail(h, B2IP_ERR_INVALID, "b2ip_add: mem=%d", mem);
+    if (n == 0) return B2IP_OK;
+    if (h->n + n >= (1ll << 32) - 1) return fail(h, B2IP_ERR_UNSUPPORTED, "a shard holds at most 2^32-2 rows");
+    Guard g(h->device);
+    RC_TRY(grow_rows(h, h->n + n));
+    float* dst = h->x32 + h->n * h->d;
+    const size_t count = static_cast<size_t>(n) * h->d;
+    const cudaMemcpyKind kind = mem == B2IP_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (src_dtype == B2IP_F32) {
+        CU_TRY(h, cudaMemcpyAsync(dst, rows, count * sizeof(float), kind, h->stream));
+    } else {
+        const __half* src = static_cast<const __half*>(rows);
+        if (mem == B2IP_MEM_HOST) {
+            RC_TRY(ensure(h, h->stage, count * sizeof(__half)));
+            CU_TRY(h, cudaMemcpyAsync(h->stage.p, rows, count * sizeof(__half), kind, h->stream));
+            src = static_cast<const __half*>(h->stage.p);
+        }
+        const int grid = static_cast<int>(std::min<size_t>((count / 2 + 255) / 256 + 1, 65535));
+        widen_f16_kernel<<<grid, 256, 0, h->stream>>>(src, dst, static_cast<long long>(count));
+    }
+    const int grid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 16));
+    shadow_rows_kernel<<<grid, 256, 0, h->stream>>>(h->x32, h->x16, h->n, h->n + n, h->d, h->d_pad,
+                                                    h->norm_stats);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->n += n;
+    return B2IP_OK;
+}
+
+int64_t b2ip_ntotal(b2ip_handle h) { return h ? h->n : -1; }
+int b2ip_dim(b2ip_handle h) { return h ? h->d : -1; }
+
+int b2ip_set_row_offset(b2ip_handle h, int64_t offset) {
+    if (!h || offset < 0) return B2IP_ERR_INVALID;
+    h->row_offset = offset;
+    return B2IP_OK;
+}
+
+int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* out_scores,
+                int64_t* out_rows, int mode, int mem) {
+    if (!h) return B2IP_ERR_INVALID;
+    if (nq < 0 || (nq > 0 && (!queries || !out_scores || !out_rows)))
+        return fail(h, B2IP_ERR_INVALID, "b2ip_search: NULL buffer or nq=%lld", (long long)nq);
+    if (k < 1) return fail(h, B2IP_ERR_INVALID, "b2ip_search: k=%d must be >= 1", k);
+    if (k > B2IP_MAX_K) return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_search: k=%d above B2IP_MAX_K=%d", k, B2IP_MAX_K);
+    if (mode < B2IP_MODE_AUTO || mode > B2IP_MODE_EXACT) return fail(h, B2IP_ERR_INVALID, "b2ip_search: mode=%d", mode);
+    if (mem != B2IP_MEM_HOST && mem != B2IP_MEM_DEVICE) return fail(h, B2IP_ERR_INVALID, "b2ip_search: mem=%d", mem);
+    if (nq >= (1ll << 31)) return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_search: nq too large");
+    Guard g(h->device);
+    if (mem == B2IP_MEM_DEVICE) return search_device(h, nq, queries, k, out_scores, out_rows, mode);
+    if (nq == 0) { memset(&h->stats, 0, sizeof(h->stats)); return B2IP_OK; }
+    RC_TRY(ensure(h, h->qstage, static_cast<size_t>(nq) * h->d * sizeof(float)));
+    RC_TRY(ensure(h, h->out_s, static_cast<size_t>(nq) * k * sizeof(float)));
+    RC_TRY(ensure(h, h->out_r, static_cast<size_t>(nq) * k * sizeof(int64_t)));
+    CU_TRY(h, cudaMemcpyAsync(h->qstage.p, queries, static_cast<size_t>(nq) * h->d * sizeof(float),
+                              cudaMemcpyHostToDevice, h->stream));
+    RC_TRY(search_device(h, nq, static_cast<const float*>(h->qstage.p), k,
+                         static_cast<float*>(h->out_s.p), static_cast<int64_t*>(h->out_r.p), mode));
+    CU_TRY(h, cudaMemcpyAsync(out_scores, h->out_s.p, static_cast<size_t>(nq) * k * sizeof(float),
+                              cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(out_rows, h->out_r.p, static_cast<size_t>(nq) * k * sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return B2IP_OK;
+}
+
+int b2ip_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int n_lists,
+                    const float* scores, const int64_t* rows, float* out_scores, int64_t* out_rows) {
+    if (nq < 0 || k < 1 || k > B2IP_MAX_K || n_lists < 1 || n_lists > 64)
+        return fail(nullptr, B2IP_ERR_INVALID, "b2ip_merge_topk: nq=%lld k=%d n_lists=%d", (long long)nq, k, n_lists);
+    if (nq == 0) return B2IP_OK;
+    if (!scores || !rows || !out_scores || !out_rows) return fail(nullptr, B2IP_ERR_INVALID, "b2ip_merge_topk: NULL buffer");
+    Guard g(device);
+    int P = 2;
+    while (P < n_lists * k) P <<= 1;
+    const size_t smem = static_cast<size_t>(P) * sizeof(unsigned long long);
+    if (smem > 200 * 1024) return fail(nullptr, B2IP_ERR_UNSUPPORTED, "b2ip_merge_topk: n_lists*k=%d too large", n_lists * k);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) {
+        merge_topk_kernel<<<static_cast<unsigned int>(nq), SEL_THREADS, smem, st>>>(
+            nq, k, n_lists, scores, reinterpret_cast<const long long*>(rows), out_scores,
+            reinterpret_cast<long long*>(out_rows), P);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, B2IP_ERR_CUDA, "b2ip_merge_topk: %s", cudaGetErrorString(e)); }
+    return B2IP_OK;
+}
+
+int b2ip_export_rows(b2ip_handle h, int64_t row0, int64_t n, float* out, int mem) {
+    if (!h) return B2IP_ERR_INVALID;
+    if (row0 < 0 || n < 0 || row0 + n > h->n || (n > 0 && !out))
+        return fail(h, B2IP_ERR_INVALID, "b2ip_export_rows: [%lld,+%lld) outside [0,%lld)", (long long)row0, (long long)n, (long long)h->n);
+    if (n == 0) return B2IP_OK;
+    Guard g(h->device);
+    CU_TRY(h, cudaMemcpyAsync(out, h->x32 + row0 * h->d, static_cast<size_t>(n) * h->d * sizeof(float),
+                              mem == B2IP_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return B2IP_OK;
+}
+
+int b2ip_stats(b2ip_handle h, b2ip_stats_t* out) {
+    if (!h || !out) return B2IP_ERR_INVALID;
+    *out = h->stats;
+    return B2IP_OK;
+}
+
+const char* b2ip_last_error(b2ip_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev, int64_t row0,
+                             int64_t n_rows, float* out_dev) {
+    if (!h || nq <= 0 || !queries_dev || !out_dev || row0 < 0 || n_rows <= 0 || row0 + n_rows > h->n)
+        return fail(h, B2IP_ERR_INVALID, "b2ip_debug_coarse_scores: bad arguments");
+    if (row0 % TILE_X != 0) return fail(h, B2IP_ERR_INVALID, "row0 must be a multiple of %d", TILE_X);
+    Guard g(h->device);
+    RC_TRY(ensure(h, h->q16, static_cast<size_t>(nq) * h->d_pad * 2));
+    RC_TRY(ensure(h, h->eps2, nq * sizeof(float)));
+    RC_TRY(ensure(h, h->thr, nq * sizeof(float)));
+    RC_TRY(ensure(h, h->cnt, nq * sizeof(int)));
+    RC_TRY(ensure(h, h->kept, nq * sizeof(int)));
+    RC_TRY(ensure(h, h->flags, nq * sizeof(int)));
+    prep_queries_kernel<<<static_cast<int>((nq + 7) / 8), 256, 0, h->stream>>>(
+        queries_dev, reinterpret_cast<__nv_bfloat16*>(h->q16.p), static_cast<int>(nq), h->d, h->d_pad,
+        h->norm_stats, reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
+        reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p), reinterpret_cast<int*>(h->flags.p));
+    CUtensorMap tmap_q, tmap_x;
+    RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, nq, h->d_pad, TILE_Q));
+    RC_TRY(make_tmap_bf16(h, &tmap_x, h->x16, h->n, h->d_pad, TILE_X));
+    CU_TRY(h, cudaFuncSetAttribute(coarse_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   COARSE_SMEM_BYTES));
+    CoarseParams cp{};
+    cp.num_k_blocks = h->d_pad / KBLOCK_ELEMS;
+    cp.q_tiles = static_cast<int>((nq + TILE_Q - 1) / TILE_Q);
+    cp.x_tiles = static_cast<int>((n_rows + TILE_X - 1) / TILE_X);
+    cp.gx = h->gx;
+    cp.nq = static_cast<int>(nq);
+    cp.x_row0 = row0;
+    cp.x_row_end = row0 + n_rows;
+    cp.thr = nullptr; cp.cand = nullptr; cp.cnt = nullptr; cp.cap = 0;
+    cp.dump = out_dev;
+    cp.dump_ld = n_rows;
+    const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
+    const int grid = static_cast<int>(std::min<long long>(tiles, h->sm_count));
+    coarse_filter_kernel<true><<<grid, COARSE_THREADS, COARSE_SMEM_BYTES, h->stream>>>(tmap_q, tmap_x, cp);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return B2IP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+// coarse_kernel.cuh -- the scoring kernel of the tensor path.
+//
+// S = Q . X^T on the 5th-gen tensor cores (tcgen05.mma kind::f16, bf16 operands, fp32
+// accumulate in TMEM) with the accumulator tile consumed in place by a per-query threshold
+// filter: the score matrix never reaches HBM, only (score,row) pairs that beat the query's
+// current threshold are appended to that query's candidate list.
+//
+// Replaces the sgemm + result-handler pair inside faiss::IndexFlatIP::search that the
+// reference calls at src/index.py:42 (exhaustive_inner_product_blas).
+//
+// CTA = 256 threads, one CTA per SM (persistent over a static tile schedule):
+//   warp 0 / lane 0 : TMA producer   (Q tile 128x64 + X tile 256x64 bf16 per k-block)
+//   warp 1 / lane 0 : MMA issuer     (4 x tcgen05.mma 128x256x16 per k-block)
+//   warp 2          : TMEM allocator (512 columns = 2 accumulator stages of 128x256 fp32)
+//   warps 4..7      : filter epilogue (thread = query row; tcgen05.ld 32 columns at a time)
+// Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA, and a
+// 2-deep TMEM ring (tmem_full/tmem_empty) between MMA and the epilogue, so the filter of
+// tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "ptx_sm100.cuh"
+#include "keys.cuh"
+
+namespace b2ip {
+
+constexpr int TILE_Q = 128;          // UMMA M  (queries per tile)
+constexpr int TILE_X = 256;          // UMMA N  (corpus rows per tile)
+constexpr int KBLOCK_BYTES = 128;    // one SWIZZLE_128B row: 64 bf16
+constexpr int KBLOCK_ELEMS = 64;
+constexpr int UMMA_K_BYTES = 32;     // 16 bf16 per tcgen05.mma
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = TILE_Q * KBLOCK_BYTES;   // 16 KiB
+constexpr int B_STAGE_BYTES = TILE_X * KBLOCK_BYTES;   // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int COARSE_THREADS = 256;
+constexpr int COARSE_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t IDESC_BF16 = ptx::umma_idesc(/*bf16*/ 1, TILE_Q, TILE_X);
+
+struct CoarseParams {
+    int num_k_blocks;        // d_pad / 64
+    int q_tiles;             // ceil(nq / 128)
+    int x_tiles;             // tiles of 256 rows in this launch
+    int gx;                  // x tiles per raster group (L2 reuse)
+    int nq;
+    long long x_row0;        // first corpus row of the launch (local row id)
+    long long x_row_end;     // one past the last row that may be reported
+    const float* thr;        // [nq] current per-query admission threshold (strict >)
+    unsigned long long* cand;  // [nq, cap] candidate keys
+    int* cnt;                // [nq] fill counters (may run past cap: overflow marker)
+    int cap;
+    float* dump;             // debug: [nq, dump_ld] raw scores, or nullptr
+    long long dump_ld;
+};
+
+__device__ __forceinline__ void tile_coords(const CoarseParams& p, int t, int& qt, int& xt) {
+    const int per_group = p.gx * p.q_tiles;
+    const int xg = t / per_group;
+    const int r = t - xg * per_group;
+    const int rem = p.x_tiles - xg * p.gx;
+    const int gx_eff = rem < p.gx ? rem : p.gx;
+    qt = r / gx_eff;
+    xt = xg * p.gx + (r - qt * gx_eff);
+}
+
+template <bool kDump>
+__global__ void __launch_bounds__(COARSE_THREADS, 1)
+coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                     const __grid_constant__ CUtensorMap tmap_x, const CoarseParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operand tiles need 1024-byte alignment.
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                 // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.q_tiles * p.x_tiles;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_q);
+        ptx::prefetch_tmap(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 128);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int qt, xt;
+                tile_coords(p, t, qt, xt);
+                const int q_row = qt * TILE_Q;
+                const long long x_row = p.x_row0 + static_cast<long long>(xt) * TILE_X;
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    ptx::tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_q, &full_bar[stage],
+                                     kb * KBLOCK_ELEMS, q_row, ptx::kEvictLast);
+                    ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_x, &full_bar[stage],
+                                     kb * KBLOCK_ELEMS, static_cast<int32_t>(x_row),
+                                     ptx::kEvictNormal);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * TILE_X);
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem_a + stage * A_STAGE_BYTES);
+                    const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < KBLOCK_BYTES / UMMA_K_BYTES; k++) {
+                        const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr + k * UMMA_K_BYTES);
+                        const uint64_t bdesc = ptx::umma_desc_k_sw128(b_addr + k * UMMA_K_BYTES);
+                        ptx::mma_f16_ss(d_tmem, adesc, bdesc, IDESC_BF16, (kb | k) != 0);
+                    }
+                    ptx::tc_commit(&empty_bar[stage]);   // smem slot reusable once MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::tc_commit(&tfull_bar[as]);          // accumulator complete
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== filter epilogue =====================
+        const int wq = warp & 3;                         // TMEM lane quarter of this warp
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int qt, xt;
+            tile_coords(p, t, qt, xt);
+            const int q = qt * TILE_Q + wq * 32 + lane;
+            const long long x_row = p.x_row0 + static_cast<long long>(xt) * TILE_X;
+            const long long left = p.x_row_end - x_row;
+            const int n_valid = left < TILE_X ? static_cast<int>(left) : TILE_X;
+            float thr = __int_as_float(0x7f800000);      // +inf: padding rows never report
+            if (q < p.nq) thr = kDump ? 0.f : __ldg(p.thr + q);
+
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * TILE_X);
+#pragma unroll 1
+            for (int c = 0; c < TILE_X / 32; c++) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(taddr + c * 32, v);
+                ptx::tmem_ld_wait();
+                if (kDump) {
+                    if (q < p.nq) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int col = c * 32 + j;
+                            if (col < n_valid)
+                                p.dump[static_cast<long long>(q) * p.dump_ld +
+                                       static_cast<long long>(xt) * TILE_X + col] = __uint_as_float(v[j]);
+                        }
+                    }
+                } else {
+                    float m = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(v[j]));
+                    if (m > thr) {
+                        // rare path: at least one of this thread's 32 scores is a candidate
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float s = __uint_as_float(v[j]);
+                            const int col = c * 32 + j;
+                            if (s > thr && col < n_valid) {
+                                const int slot = atomicAdd(p.cnt + q, 1);
+                                if (slot < p.cap)
+                                    p.cand[static_cast<long long>(q) * p.cap + slot] =
+                                        make_key(s, static_cast<uint32_t>(x_row + col));
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace b2ip

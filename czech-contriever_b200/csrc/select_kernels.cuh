@@ -1,0 +1,551 @@
+// select_kernels.cuh -- everything around the scoring kernel: corpus/query preparation
+// (bf16 shadow + rigorous error bound), the per-slab threshold refresh (radix select over a
+// query's candidate list), the fp32 rescore + final sort, the exact fp32 path used as the
+// overflow fallback, and the multi-shard merge.
+//
+// Together with coarse_kernel.cuh these replace faiss's result handlers
+// (HeapBlockResultHandler / ReservoirBlockResultHandler) that the reference
+// reaches through src/index.py:42.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <float.h>
+#include "keys.cuh"
+
+namespace b2ip {
+
+constexpr int SEL_THREADS = 256;
+constexpr int SORT_CAP = 4096;       // u64 keys sorted in shared memory by finalize
+constexpr int FLAG_OVERFLOW = 1;
+constexpr int EXACT_QB = 8;          // queries per pass of the exact path
+
+// device-side counters of one search (int64 each)
+enum { GS_MAX_KEPT = 0, GS_OVERFLOW = 1, GS_CANDIDATES = 2, GS_RESCORED = 3, GS_COUNT = 4 };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// corpus ingest
+// ---------------------------------------------------------------------------------------
+__global__ void widen_f16_kernel(const __half* __restrict__ src, float* __restrict__ dst,
+                                 long long count) {
+    long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x * 2;
+    for (; i + 1 < count; i += step) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(src + i));
+        *reinterpret_cast<float2*>(dst + i) = f;
+    }
+    if (i < count && i + 1 >= count) dst[i] = __half2float(src[i]);
+}
+
+// One warp per row: bf16 shadow (zero padded to d_pad) + max ||x||^2 and max ||x - bf16(x)||^2
+// over all rows, which feed the per-query error bound of the coarse scores.
+__global__ void shadow_rows_kernel(const float* __restrict__ x32, __nv_bfloat16* __restrict__ x16,
+                                   long long row0, long long row1, int d, int d_pad,
+                                   unsigned int* __restrict__ norm_stats) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    float mx = 0.f, md = 0.f;
+    for (long long r = row0 + warp; r < row1; r += nwarps) {
+        const float4* src = reinterpret_cast<const float4*>(x32 + r * d);
+        uint2* dst = reinterpret_cast<uint2*>(x16 + r * d_pad);
+        float nx = 0.f, nd = 0.f;
+        for (int j = lane; j < d_pad / 4; j += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < d / 4) v = __ldg(src + j);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+            const float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);
+            const float e0 = v.x - flo.x, e1 = v.y - flo.y, e2 = v.z - fhi.x, e3 = v.w - fhi.y;
+            nx += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            nd += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+            uint2 o;
+            o.x = *reinterpret_cast<const unsigned int*>(&lo);
+            o.y = *reinterpret_cast<const unsigned int*>(&hi);
+            dst[j] = o;
+        }
+        nx = warp_sum(nx);
+        nd = warp_sum(nd);
+        if (nx == nx) mx = fmaxf(mx, nx);   // NaN rows never score, keep them out of the bound
+        if (nd == nd) md = fmaxf(md, nd);
+    }
+    if (lane == 0) {
+        // non-negative floats order like their bit patterns
+        atomicMax(norm_stats + 0, __float_as_uint(mx));
+        atomicMax(norm_stats + 1, __float_as_uint(md));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// query preparation: bf16 copy + eps2[q] = 2 * bound(|coarse - exact|), state reset
+// ---------------------------------------------------------------------------------------
+// |q.x - bf(q).bf(x)| = |bf(q).(x - bf(x)) + (q - bf(q)).x|
+//                    <= ||bf(q)|| * max||x - bf(x)|| + ||q - bf(q)|| * max||x||      (Cauchy-Schwarz)
+// plus a slack for the tensor core's fp32 accumulation: d_pad * 2^-23 * ||bf(q)|| * max||bf(x)||.
+__global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16* __restrict__ q16,
+                                    int nq, int d, int d_pad,
+                                    const unsigned int* __restrict__ norm_stats,
+                                    float* __restrict__ eps2, float* __restrict__ thr,
+                                    int* __restrict__ cnt, int* __restrict__ kept,
+                                    int* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    const float4* src = reinterpret_cast<const float4*>(q32 + static_cast<long long>(q) * d);
+    uint2* dst = reinterpret_cast<uint2*>(q16 + static_cast<long long>(q) * d_pad);
+    float nh = 0.f, nd = 0.f;
+    for (int j = lane; j < d_pad / 4; j += 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < d / 4) v = __ldg(src + j);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        const float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);
+        const float e0 = v.x - flo.x, e1 = v.y - flo.y, e2 = v.z - fhi.x, e3 = v.w - fhi.y;
+        nh += flo.x * flo.x + flo.y * flo.y + fhi.x * fhi.x + fhi.y * fhi.y;
+        nd += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+        uint2 o;
+        o.x = *reinterpret_cast<const unsigned int*>(&lo);
+        o.y = *reinterpret_cast<const unsigned int*>(&hi);
+        dst[j] = o;
+    }
+    nh = warp_sum(nh);
+    nd = warp_sum(nd);
+    if (lane == 0) {
+        const float nx = sqrtf(__uint_as_float(norm_stats[0]));
+        const float dx = sqrtf(__uint_as_float(norm_stats[1]));
+        const float qh = sqrtf(nh), dq = sqrtf(nd);
+        const float acc = static_cast<float>(d_pad) * 1.1920929e-7f;   // d_pad * 2^-23
+        float e = qh * dx + dq * nx + acc * qh * (nx + dx);
+        e = e * 1.001f + FLT_MIN;          // norms above were themselves rounded
+        eps2[q] = 2.f * e;
+        thr[q] = -INFINITY;
+        cnt[q] = 0;
+        kept[q] = 0;
+        flags[q] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// block-wide radix select
+// ---------------------------------------------------------------------------------------
+// Top `n_bytes` bytes of the k-th largest of keys[0..n) (1 <= k <= n); low bytes are zero.
+// With n_bytes = 4 that is the k-th largest SCORE, with 8 the k-th largest key.
+__device__ unsigned long long block_radix_select(const unsigned long long* __restrict__ keys,
+                                                 int n, int k, int n_bytes, unsigned int* hist,
+                                                 unsigned long long* s_prefix, int* s_krem) {
+    unsigned long long prefix = 0;
+    int krem = k;
+    for (int pass = 0; pass < n_bytes; pass++) {
+        const int shift = 56 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            unsigned int c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { c[j] = hist[255 - (8 * lane + j)]; sum += c[j]; }
+            unsigned int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const unsigned int excl = incl - sum;
+            if (excl < static_cast<unsigned int>(krem) && static_cast<unsigned int>(krem) <= incl) {
+                unsigned int r = krem - excl;
+                int digit = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (r <= c[j]) { digit = 255 - (8 * lane + j); break; }
+                    r -= c[j];
+                }
+                *s_prefix = prefix | (static_cast<unsigned long long>(digit) << shift);
+                *s_krem = static_cast<int>(r);
+            }
+        }
+        __syncthreads();
+        prefix = *s_prefix;
+        krem = *s_krem;
+    }
+    return prefix;
+}
+
+// In-place stream compaction of keys[0..n): keeps keys whose high word is > hi_thr
+// (or, with by_key, keys >= key_thr).  Returns the number kept (all threads).
+__device__ int block_compact(unsigned long long* keys, int n, bool by_key, uint32_t hi_thr,
+                             unsigned long long key_thr, unsigned long long* out, int* s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int base_out = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        unsigned long long key = 0;
+        bool keep = false;
+        if (i < n) {
+            key = keys[i];
+            keep = by_key ? (key >= key_thr) : (static_cast<uint32_t>(key >> 32) > hi_thr);
+        }
+        const unsigned int ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(ballot);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int w = 0; w < nw; w++) {
+            const int c = s_warp[w];
+            if (w < warp) off += c;
+            tot += c;
+        }
+        if (keep) out[base_out + off + __popc(ballot & ((1u << lane) - 1u))] = key;
+        base_out += tot;
+        __syncthreads();
+    }
+    return base_out;
+}
+
+// ---------------------------------------------------------------------------------------
+// threshold refresh after a slab: one CTA per query
+// ---------------------------------------------------------------------------------------
+// Let c_k be the k-th largest COARSE score seen so far.  k rows have exact score >= c_k - eps,
+// so every member of the final exact top-k has exact >= c_k - eps and coarse >= c_k - 2 eps:
+// rows below that can be dropped for good, and later slabs only need to report above it.
+__global__ void __launch_bounds__(SEL_THREADS)
+refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
+                         int* __restrict__ cnt, int* __restrict__ kept, float* __restrict__ thr,
+                         const float* __restrict__ eps2, int* __restrict__ flags,
+                         long long* __restrict__ gstats) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_krem;
+    __shared__ int s_warp[SEL_THREADS / 32];
+    const int q = blockIdx.x;
+    if (flags[q] & FLAG_OVERFLOW) return;
+    const int n = cnt[q];
+    const int prev = kept[q];
+    if (n > cap) {
+        // more hits than the list holds: this query is re-run on the exact path
+        if (threadIdx.x == 0) {
+            flags[q] |= FLAG_OVERFLOW;
+            thr[q] = INFINITY;
+            cnt[q] = 0;
+            kept[q] = 0;
+            atomicAdd(reinterpret_cast<unsigned long long*>(gstats + GS_OVERFLOW), 1ull);
+        }
+        return;
+    }
+    if (n == prev) return;
+    if (threadIdx.x == 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(gstats + GS_CANDIDATES),
+                  static_cast<unsigned long long>(n - prev));
+    if (n < k) {
+        if (threadIdx.x == 0) kept[q] = n;
+        return;
+    }
+    unsigned long long* keys = cand + static_cast<long long>(q) * cap;
+    const unsigned long long pk = block_radix_select(keys, n, k, 4, hist, &s_prefix, &s_krem);
+    const float ck = unorder_f32(static_cast<uint32_t>(pk >> 32));
+    float t = __fsub_rd(ck, eps2[q]);
+    t = nextafterf(t, -INFINITY);                    // admission test is strict
+    const int m = block_compact(keys, n, false, order_f32(t), 0ull, keys, s_warp);
+    if (threadIdx.x == 0) {
+        cnt[q] = m;
+        kept[q] = m;
+        thr[q] = t;
+        atomicMax(reinterpret_cast<unsigned long long*>(gstats + GS_MAX_KEPT),
+                  static_cast<unsigned long long>(m));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize: (optional) fp32 rescore of the surviving candidates, exact top-k, sorted output
+// ---------------------------------------------------------------------------------------
+struct FinalizeParams {
+    int k, cap, d;
+    const int* qlist;                 // slot -> query index (nullptr: identity)
+    unsigned long long* cand;         // [slots, cap]
+    const int* cnt;                   // [slots] entries per slot
+    const int* flags;                 // [slots] or nullptr
+    const float* q32;                 // [*, d] fp32 queries (rescore)
+    const float* x32;                 // [n, d] fp32 corpus (rescore)
+    long long row_offset;
+    float* out_scores;                // [*, k]
+    long long* out_rows;              // [*, k]
+    long long* gstats;
+};
+
+__device__ void block_bitonic_desc(unsigned long long* s, int P) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < P / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long a = s[lo], b = s[hi];
+                if ((a < b) == desc) { s[lo] = b; s[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <bool kRescore>
+__global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizeParams p) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(fsm);   // [SORT_CAP]
+    float* sq = reinterpret_cast<float*>(fsm + SORT_CAP * sizeof(unsigned long long));  // [d]
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_krem;
+    __shared__ int s_warp[SEL_THREADS / 32];
+
+    const int slot = blockIdx.x;
+    if (p.flags && (p.flags[slot] & FLAG_OVERFLOW)) return;
+    const int q = p.qlist ? p.qlist[slot] : slot;
+    const int n = min(p.cnt[slot], p.cap);
+    unsigned long long* keys = p.cand + static_cast<long long>(slot) * p.cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+    if (kRescore) {
+        for (int j = threadIdx.x; j < p.d; j += blockDim.x)
+            sq[j] = p.q32[static_cast<long long>(q) * p.d + j];
+        __syncthreads();
+        const float4* q4 = reinterpret_cast<const float4*>(sq);
+        for (int i = warp; i < n; i += nw) {
+            const uint32_t row = key_row(keys[i]);
+            const float4* xr = reinterpret_cast<const float4*>(p.x32 + static_cast<long long>(row) * p.d);
+            double acc = 0.0;
+            for (int j = lane; j < p.d / 4; j += 32) {
+                const float4 a = __ldg(xr + j);
+                const float4 b = q4[j];
+                acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
+                acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
+                acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
+                acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) keys[i] = make_key(static_cast<float>(acc), row);   // NaN -> high word 0
+        }
+        if (threadIdx.x == 0 && p.gstats)
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.gstats + GS_RESCORED),
+                      static_cast<unsigned long long>(n));
+        __syncthreads();
+    }
+
+    int m;   // entries to sort
+    if (n <= SORT_CAP) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sbuf[i] = keys[i];
+        m = n;
+    } else {
+        // more survivors than the sort buffer: radix-select the k best keys first
+        const unsigned long long kth = block_radix_select(keys, n, p.k, 8, hist, &s_prefix, &s_krem);
+        m = block_compact(keys, n, true, 0u, kth, sbuf, s_warp);
+    }
+    int P = 1;
+    while (P < m) P <<= 1;
+    if (P < 2) P = 2;
+    for (int i = m + threadIdx.x; i < P; i += blockDim.x) sbuf[i] = 0ull;
+    __syncthreads();
+    block_bitonic_desc(sbuf, P);
+    for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
+        float s = -FLT_MAX;
+        long long r = -1;
+        if (j < m) {
+            const unsigned long long key = sbuf[j];
+            if ((key >> 32) != 0ull) { s = key_score(key); r = static_cast<long long>(key_row(key)) + p.row_offset; }
+        }
+        p.out_scores[static_cast<long long>(q) * p.k + j] = s;
+        p.out_rows[static_cast<long long>(q) * p.k + j] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// exact path: fp32 FMA scores for up to EXACT_QB queries, then a multi-CTA radix select
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+exact_scores_kernel(const float* __restrict__ x32, long long n, int d,
+                    const float* __restrict__ q32, const int* __restrict__ qlist, int nqg,
+                    float* __restrict__ scores /*[EXACT_QB, n]*/) {
+    extern __shared__ __align__(16) float esq[];   // [EXACT_QB, d]
+    for (int i = threadIdx.x; i < EXACT_QB * d; i += blockDim.x) {
+        const int b = i / d, j = i - b * d;
+        esq[i] = b < nqg ? q32[static_cast<long long>(qlist[b]) * d + j] : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int d4 = d / 4;
+    const float4* sq4 = reinterpret_cast<const float4*>(esq);
+    for (long long r = warp; r < n; r += nwarps) {
+        const float4* xr = reinterpret_cast<const float4*>(x32 + r * d);
+        float acc[EXACT_QB];
+#pragma unroll
+        for (int b = 0; b < EXACT_QB; b++) acc[b] = 0.f;
+        for (int j = lane; j < d4; j += 32) {
+            const float4 xv = __ldg(xr + j);
+#pragma unroll
+            for (int b = 0; b < EXACT_QB; b++) {
+                const float4 qv = sq4[b * d4 + j];
+                acc[b] = fmaf(xv.x, qv.x, acc[b]);
+                acc[b] = fmaf(xv.y, qv.y, acc[b]);
+                acc[b] = fmaf(xv.z, qv.z, acc[b]);
+                acc[b] = fmaf(xv.w, qv.w, acc[b]);
+            }
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int b = 0; b < EXACT_QB; b++) {
+            const float s = warp_sum(acc[b]);
+            if (lane == b) mine = s;
+        }
+        if (lane < nqg) scores[static_cast<long long>(lane) * n + r] = mine;
+    }
+}
+
+// per-query select state of the exact path
+struct ExactState {
+    unsigned long long prefix[EXACT_QB];
+    int krem[EXACT_QB];
+    int take_all[EXACT_QB];
+};
+
+__global__ void exact_init_kernel(ExactState* st, unsigned int* ghist, int* cnt, int k) {
+    const int i = threadIdx.x;
+    if (i < EXACT_QB) { st->prefix[i] = 0; st->krem[i] = k; st->take_all[i] = 0; cnt[i] = 0; }
+    for (int j = i; j < EXACT_QB * 256; j += blockDim.x) ghist[j] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+exact_hist_kernel(const float* __restrict__ scores, long long n, int pass,
+                  const ExactState* __restrict__ st, unsigned int* __restrict__ ghist) {
+    __shared__ unsigned int hist[256];
+    const int g = blockIdx.y;
+    if (st->take_all[g]) return;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+    const unsigned long long prefix = st->prefix[g];
+    const float* s = scores + static_cast<long long>(g) * n;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const unsigned long long key = make_key(s[i], static_cast<uint32_t>(i));
+        if ((key >> 32) != 0ull && (key & mask) == prefix)
+            atomicAdd(&hist[(key >> shift) & 255], 1u);
+    }
+    __syncthreads();
+    const unsigned int c = hist[threadIdx.x];
+    if (c) atomicAdd(&ghist[g * 256 + threadIdx.x], c);
+}
+
+__global__ void exact_pick_kernel(ExactState* st, unsigned int* ghist, int pass) {
+    const int g = blockIdx.x, lane = threadIdx.x;
+    if (st->take_all[g]) return;
+    unsigned int* h = ghist + g * 256;
+    const int shift = 56 - 8 * pass;
+    const int krem = st->krem[g];
+    unsigned int c[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { c[j] = h[255 - (8 * lane + j)]; sum += c[j]; }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned int excl = incl - sum;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; j++) h[255 - (8 * lane + j)] = 0;   // ready for the next pass
+    if (total < static_cast<unsigned int>(krem)) {
+        // fewer than k reportable rows in total: everything is a result
+        if (lane == 0) { st->take_all[g] = 1; st->prefix[g] = 0; }
+        return;
+    }
+    if (excl < static_cast<unsigned int>(krem) && static_cast<unsigned int>(krem) <= incl) {
+        unsigned int r = krem - excl;
+        int digit = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (r <= c[j]) { digit = 255 - (8 * lane + j); break; }
+            r -= c[j];
+        }
+        st->prefix[g] |= static_cast<unsigned long long>(digit) << shift;
+        st->krem[g] = static_cast<int>(r);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+exact_collect_kernel(const float* __restrict__ scores, long long n, const ExactState* __restrict__ st,
+                     unsigned long long* __restrict__ cand, int* __restrict__ cnt, int cap) {
+    const int g = blockIdx.y;
+    const unsigned long long kth = st->prefix[g];
+    const float* s = scores + static_cast<long long>(g) * n;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const unsigned long long key = make_key(s[i], static_cast<uint32_t>(i));
+        if ((key >> 32) != 0ull && key >= kth) {
+            const int slot = atomicAdd(cnt + g, 1);
+            if (slot < cap) cand[static_cast<long long>(g) * cap + slot] = key;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// padding for an empty index, and the multi-shard merge
+// ---------------------------------------------------------------------------------------
+__global__ void fill_padding_kernel(float* scores, long long* rows, long long count) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        scores[i] = -FLT_MAX;
+        rows[i] = -1;
+    }
+}
+
+// One CTA per query: the n_lists*k shard-local winners are sorted in shared memory by
+// (score desc, global row asc) and the first k written out.  smem: P u64 keys.
+__global__ void __launch_bounds__(SEL_THREADS)
+merge_topk_kernel(long long nq, int k, int n_lists, const float* __restrict__ scores,
+                  const long long* __restrict__ rows, float* __restrict__ out_scores,
+                  long long* __restrict__ out_rows, int P) {
+    extern __shared__ __align__(16) uint8_t msm[];
+    unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(msm);
+    const long long q = blockIdx.x;
+    const int total = n_lists * k;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < total) {
+            const int l = i / k, j = i - l * k;
+            const long long src = (static_cast<long long>(l) * nq + q) * k + j;
+            const long long r = rows[src];
+            if (r >= 0) key = make_key(scores[src], static_cast<uint32_t>(r));
+        }
+        sbuf[i] = key;
+    }
+    __syncthreads();
+    block_bitonic_desc(sbuf, P);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const unsigned long long key = sbuf[j];
+        float s = -FLT_MAX;
+        long long r = -1;
+        if ((key >> 32) != 0ull) { s = key_score(key); r = key_row(key); }
+        out_scores[q * k + j] = s;
+        out_rows[q * k + j] = r;
+    }
+}
+
+}  // namespace b2ip

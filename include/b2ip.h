@@ -1,0 +1,131 @@
+/*
+ * b2ip.h -- C ABI of libb2ip.so, the B200 (sm_100a) exact inner-product top-k engine.
+ *
+ * This is the boundary a maintainer of the reference binds instead of faiss: every entry
+ * point below replaces one faiss call made by the reference's `Indexer`
+ * (reference src/index.py) -- the citation on each function is the call it stands in for.
+ * Plain pointers and sizes only; no torch / C++ types cross the ABI; no exceptions.
+ *
+ * Conventions
+ *   - every function returns B2IP_OK (0) or a negative B2IP_ERR_* code; the message is
+ *     available from b2ip_last_error(handle) (or b2ip_last_error(NULL) for create()).
+ *   - the library owns all device memory it allocates; caller buffers are borrowed for the
+ *     duration of one call and every call is synchronous on return.
+ *   - `mem` says where a caller buffer lives: B2IP_MEM_HOST or B2IP_MEM_DEVICE (a pointer
+ *     valid on the index's device, e.g. a torch CUDA tensor's data_ptr()).
+ *   - one handle = one GPU = one row shard.  Not re-entrant per handle (the reference is
+ *     single-threaded); distinct handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device b2ip_create() fails.
+ */
+#ifndef B2IP_H_
+#define B2IP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2ip_index_s* b2ip_handle;
+
+enum {
+    B2IP_OK = 0,
+    B2IP_ERR_INVALID = -1,     /* bad argument */
+    B2IP_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+    B2IP_ERR_OOM = -3,         /* device allocation failed */
+    B2IP_ERR_UNSUPPORTED = -4, /* e.g. k above B2IP_MAX_K */
+    B2IP_ERR_INTERNAL = -5
+};
+
+enum { B2IP_F32 = 0, B2IP_F16 = 1 };           /* element type of rows handed to b2ip_add */
+enum { B2IP_MEM_HOST = 0, B2IP_MEM_DEVICE = 1 };
+
+/* search strategy */
+enum {
+    B2IP_MODE_AUTO = 0,   /* tensor path; tiny problems take the exact path            */
+    B2IP_MODE_TENSOR = 1, /* tcgen05 bf16 coarse GEMM + fused threshold filter, fp32 rescore */
+    B2IP_MODE_EXACT = 2   /* fp32 FMA scores + radix select (also the overflow fallback) */
+};
+
+#define B2IP_MAX_K 2048
+
+/* Counters of the most recent b2ip_search on a handle (timings from CUDA events on the
+ * handle's stream). */
+typedef struct b2ip_stats_s {
+    int64_t nq, ntotal;
+    int32_t k, mode_used;
+    int32_t coarse_launches;     /* launches of the tcgen05 scoring kernel                */
+    int32_t total_launches;      /* all kernels launched by the search                    */
+    float coarse_ms;             /* sum of the scoring-kernel durations                   */
+    float total_ms;              /* whole device-side search                              */
+    double coarse_flops;         /* 2*nq*rows*d summed over scoring launches (algorithmic) */
+    int64_t candidates;          /* (query,row) pairs that passed the fused filter        */
+    int64_t rescored;            /* pairs rescored in fp32                                */
+    int64_t fallback_queries;    /* queries re-run on the exact path (buffer overflow)    */
+    int32_t slabs;               /* corpus slabs (threshold refresh points)               */
+    int32_t query_batches;
+} b2ip_stats_t;
+
+/* replaces faiss.IndexFlatIP(vector_sz)                       -- src/index.py:21
+ * d: vector dimension (multiple of 4, <= 4096); device: CUDA ordinal. */
+int b2ip_create(int d, int device, b2ip_handle* out);
+
+/* drops the index and all device memory (the reference relies on GC). */
+void b2ip_destroy(b2ip_handle h);
+
+/* Run all device work of this handle on the given cudaStream_t (NULL = the handle's own
+ * stream).  Lets a torch caller keep its current stream ordering. */
+int b2ip_set_stream(b2ip_handle h, void* cuda_stream);
+
+/* Optional capacity hint before a series of b2ip_add calls (avoids regrowth copies). */
+int b2ip_reserve(b2ip_handle h, int64_t n_rows);
+
+/* replaces index.add(embeddings) after embeddings.astype('float32') -- src/index.py:27,30
+ * Appends n rows ([n,d] row-major, C-contiguous) of type src_dtype; rows get consecutive
+ * local ids ntotal .. ntotal+n-1.  fp16 input is widened exactly, as astype does. */
+int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem);
+
+/* replaces index.ntotal                                        -- src/index.py:67-68 */
+int64_t b2ip_ntotal(b2ip_handle h);
+int b2ip_dim(b2ip_handle h);
+
+/* Ids reported by b2ip_search are local row + offset (row-sharded multi-GPU: shard g
+ * passes the number of rows held by shards 0..g-1). Default 0. */
+int b2ip_set_row_offset(b2ip_handle h, int64_t offset);
+
+/* replaces scores, indexes = index.search(q, top_docs)         -- src/index.py:42
+ * queries [nq,d] fp32; out_scores [nq,k] fp32, per row descending; out_rows [nq,k] int64
+ * 0-based insertion-order ids (+ row offset).  Exact ties keep the lower row.  When fewer
+ * than k rows exist the tail is (-FLT_MAX, -1) as faiss pads.  NaN scores are never
+ * returned.  1 <= k <= B2IP_MAX_K. */
+int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* out_scores,
+                int64_t* out_rows, int mode, int mem);
+
+/* The one exchange step of the row-sharded search: merges n_lists per-shard results
+ * (scores [n_lists,nq,k] descending per list, rows [n_lists,nq,k] global ids, -1 padded)
+ * into the global top-k (score desc, ties -> lower row).  All pointers are DEVICE
+ * pointers on `device`; runs on `cuda_stream` and synchronises it before returning. */
+int b2ip_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int n_lists,
+                    const float* scores, const int64_t* rows, float* out_scores,
+                    int64_t* out_rows);
+
+/* replaces faiss.write_index's read of the stored vectors       -- src/index.py:53
+ * Copies rows [row0, row0+n) as fp32 into out ([n,d]). */
+int b2ip_export_rows(b2ip_handle h, int64_t row0, int64_t n, float* out, int mem);
+
+int b2ip_stats(b2ip_handle h, b2ip_stats_t* out);
+const char* b2ip_last_error(b2ip_handle h);
+
+/* Test hook: raw bf16 tensor-core scores of queries [nq,d] (device fp32) against rows
+ * [row0,row0+n_rows) written to out [nq,n_rows] (device fp32) by the same tcgen05
+ * mainloop the search uses (filter replaced by a store). */
+int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev, int64_t row0,
+                             int64_t n_rows, float* out_dev);
+
+/* Library build info: "b2ip <version> sm_100a ..." */
+const char* b2ip_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2IP_H_ */

@@ -1,0 +1,288 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libb2ip.so), against
+the CPU oracle (oracle/flatip_oracle.c) on the same seeded inputs.
+
+Acceptance (BASELINE.json north_star): identical top-k index sets, differences only among
+ties whose scores are within 1e-5 relative; scores within 1e-5 relative
+(oracle.flatip_oracle.compare_topk, rtol = 1e-5)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from helpers import ingest_like_reference_driver, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def fo():
+    from oracle import flatip_oracle
+    return flatip_oracle
+
+
+def _engine(x, device=0):
+    from b2ip import Engine
+    e = Engine(x.shape[1], device)
+    e.add(x)
+    return e
+
+
+def test_library_reports_sm100():
+    import b2ip
+    assert b"sm_100a" in b2ip.load().b2ip_version()
+
+
+def test_coarse_scores_match_bf16_matmul():
+    """The tcgen05 mainloop alone: raw scores vs torch on the same bf16-rounded operands."""
+    import torch
+    x = synth(1000, 768, 1234)
+    q = synth(200, 768, 4321)
+    e = _engine(x)
+    qt = torch.from_numpy(q).cuda()
+    got = e.debug_coarse_scores(qt, 0, 1000).cpu().numpy()
+    xr = torch.from_numpy(x).cuda().bfloat16().float()
+    qr = qt.bfloat16().float()
+    want = (qr.double() @ xr.double().T).float().cpu().numpy()
+    # products of bf16 values are exact in fp32; only the accumulation order differs
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
+    # second call at a row offset (multiple of the 256-row tile)
+    got2 = e.debug_coarse_scores(qt, 512, 488).cpu().numpy()
+    np.testing.assert_allclose(got2, want[:, 512:], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("mode", ["tensor", "exact"])
+@pytest.mark.parametrize("n,nq,k,d", [
+    (5000, 64, 100, 768),
+    (20000, 300, 10, 768),
+    (3000, 33, 1, 64),
+    (4097, 129, 99, 128),
+    (10000, 17, 101, 768),
+    (30000, 50, 1000, 256),
+    (257, 5, 100, 768),
+])
+def test_search_matches_oracle(fo, mode, n, nq, k, d):
+    x = synth(n, d, 1234)
+    q = synth(nq, d, 4321)
+    e = _engine(x)
+    D, I = e.search(q, k, mode=mode)
+    Do, Io = fo.search(q, x, k)
+    assert D.dtype == np.float32 and I.dtype == np.int64
+    assert (np.diff(D, axis=1) <= 0).all(), "rows must be score-descending"
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+    st = e.stats()
+    assert st["nq"] == nq and st["ntotal"] == n
+    if mode == "tensor":
+        assert st["coarse_launches"] >= 1 and st["fallback_queries"] == 0
+
+
+def test_c1_full_config(fo):
+    """BASELINE config 1 in full: 100k x 768 corpus, 1k queries, k=100."""
+    x = synth(100_000, 768, 1234)
+    q = synth(1000, 768, 4321)
+    e = _engine(x)
+    D, I = e.search(q, 100)
+    Do, Io = fo.search(q, x, 100)
+    r = fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+    assert r["queries"] == 1000
+
+
+@pytest.mark.parametrize("mode", ["tensor", "exact"])
+def test_fewer_rows_than_k_pads_like_faiss(fo, mode):
+    x = synth(37, 768, 1)
+    q = synth(9, 768, 2)
+    e = _engine(x)
+    D, I = e.search(q, 100, mode=mode)
+    Do, Io = fo.search(q, x, 100)
+    assert (I[:, 37:] == -1).all() and (D[:, 37:] == np.finfo(np.float32).min).all()
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+
+
+def test_empty_index_and_empty_queries():
+    from b2ip import Engine
+    e = Engine(768, 0)
+    D, I = e.search(synth(3, 768, 0), 10)
+    assert (I == -1).all() and (D == np.finfo(np.float32).min).all()
+    e.add(synth(100, 768, 1))
+    D, I = e.search(np.zeros((0, 768), np.float32), 10)
+    assert D.shape == (0, 10) and I.shape == (0, 10)
+
+
+@pytest.mark.parametrize("mode", ["tensor", "exact"])
+def test_duplicate_rows_keep_lower_row(fo, mode):
+    """Exact ties: faiss's strict insertion keeps the earlier (lower) row at the boundary."""
+    base = synth(40, 128, 7)
+    x = np.tile(base, (20, 1))            # every row appears 20 times
+    q = synth(12, 128, 8)
+    e = _engine(x)
+    D, I = e.search(q, 50, mode=mode)
+    D64, I64 = fo.brute_force_f64(q, x, 50)   # stable: score desc, row asc
+    fo.compare_topk(D, I, D64.astype(np.float32), I64, q, x, rtol=RTOL)
+    # among equal scores our order is row-ascending and the k-th boundary keeps lower rows
+    assert np.array_equal(I, I64)
+
+
+def test_identity_corpus_known_answer():
+    d = 768
+    x = np.eye(d, dtype=np.float32)
+    q = synth(16, d, 3, normalize=False)
+    e = _engine(x)
+    D, I = e.search(q, 10)
+    want = np.argsort(-q, axis=1, kind="stable")[:, :10]
+    assert np.array_equal(I, want)
+    np.testing.assert_allclose(D, np.take_along_axis(q, want, axis=1), rtol=1e-6)
+
+
+def test_overflowing_candidate_lists_fall_back_exactly(fo):
+    """All-equal corpus: every row ties with the threshold, the candidate lists overflow and
+    the queries are re-run on the exact path -- still the right answer (rows 0..k-1)."""
+    x = np.tile(synth(1, 256, 5), (20000, 1))
+    q = synth(6, 256, 6)
+    e = _engine(x)
+    D, I = e.search(q, 100, mode="tensor")
+    assert e.stats()["fallback_queries"] == 6
+    assert np.array_equal(I, np.tile(np.arange(100), (6, 1)))
+    Do, Io = fo.search(q, x, 100)
+    np.testing.assert_allclose(D, Do, rtol=RTOL)
+
+
+def test_unnormalised_and_fp16_inputs(fo):
+    """Real pipeline data: fp16 arrays (generate_passage_embeddings.py:75-76), not normalised."""
+    x = (synth(8000, 768, 11, normalize=False) * 0.3).astype(np.float16)
+    q = (synth(40, 768, 12, normalize=False) * 0.3).astype(np.float16)
+    e = _engine(x)
+    D, I = e.search(q.astype(np.float32), 100)
+    Do, Io = fo.search(q.astype(np.float32), x.astype(np.float32), 100)
+    fo.compare_topk(D, I, Do, Io, q.astype(np.float32), x.astype(np.float32), rtol=RTOL)
+    np.testing.assert_array_equal(e.export_rows(10, 5), x[10:15].astype(np.float32))
+
+
+def test_incremental_adds_equal_one_add(fo):
+    x = synth(7000, 768, 21)
+    q = synth(20, 768, 22)
+    from b2ip import Engine
+    e = Engine(768, 0)
+    for a, b in [(0, 1), (1, 300), (300, 4096), (4096, 7000)]:
+        e.add(x[a:b])
+    assert e.ntotal == 7000
+    D, I = e.search(q, 100)
+    Do, Io = fo.search(q, x, 100)
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+
+
+def test_torch_device_buffers(fo):
+    import torch
+    x = synth(6000, 768, 31)
+    q = synth(70, 768, 32)
+    from b2ip import Engine
+    e = Engine(768, 0)
+    e.add(torch.from_numpy(x).cuda())
+    D, I = e.search(torch.from_numpy(q).cuda(), 100)
+    Do, Io = fo.search(q, x, 100)
+    fo.compare_topk(D.cpu().numpy(), I.cpu().numpy(), Do, Io, q, x, rtol=RTOL)
+
+
+def test_merge_topk_and_sharded_equals_single(fo):
+    """Two row shards on one GPU + merge kernel == one index (the multi-GPU path minus NCCL)."""
+    import torch
+    from b2ip import Engine, merge_topk
+    x = synth(9000, 768, 41)
+    q = synth(64, 768, 42)
+    k = 100
+    whole = _engine(x)
+    Dw, Iw = whole.search(q, k)
+    parts = []
+    for lo, hi in [(0, 4000), (4000, 9000)]:
+        e = Engine(768, 0)
+        e.add(x[lo:hi])
+        e.set_row_offset(lo)
+        parts.append(e.search(torch.from_numpy(q).cuda(), k))
+    gD = torch.stack([p[0] for p in parts])
+    gI = torch.stack([p[1] for p in parts])
+    D, I = merge_topk(gD, gI, k)
+    assert np.array_equal(I.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dw)
+
+
+def test_indexer_drop_in(fo, tmp_path):
+    """Same calls on the B200 `Indexer` and on the oracle's restatement of the reference one:
+    pickle shards -> driver ingest loop -> search_knn -> serialize -> deserialize_from."""
+    from src.index import Indexer
+    d, k = 768, 100
+    shards = []
+    start = 0
+    for i, n in enumerate([1500, 700, 2300]):
+        emb = synth(n, d, 100 + i, normalize=False).astype(np.float16)
+        ids = [str(start + j) for j in range(n)]          # str ids, as load_passages yields
+        path = tmp_path / f"passages_{i:02d}"
+        with open(path, "wb") as f:
+            pickle.dump((ids, emb), f)                    # generate_passage_embeddings.py:94-95
+        start += n
+    files = sorted(str(p) for p in tmp_path.glob("passages_*"))
+    for f in files:
+        with open(f, "rb") as fin:
+            shards.append(pickle.load(fin))
+    ours, ref = Indexer(d, 0, 8), fo.OracleIndexer(d, 0, 8)
+    ingest_like_reference_driver(ours, shards, 1000)
+    ingest_like_reference_driver(ref, shards, 1000)
+    assert ours.index_id_to_db_id == ref.index_id_to_db_id
+    q = synth(50, d, 777, normalize=False).astype(np.float16)
+    got, want = ours.search_knn(q, k), ref.search_knn(q, k)
+    assert len(got) == len(want) == 50
+    x = ref.rows
+    for (gi, gs), (wi, ws) in zip(got, want):
+        assert isinstance(gi, list) and isinstance(gi[0], str) and gs.dtype == np.float32
+        assert gs.shape == (k,)
+    fo.compare_topk(np.stack([g[1] for g in got]), np.array([[int(s) for s in g[0]] for g in got]),
+                    np.stack([w[1] for w in want]), np.array([[int(s) for s in w[0]] for w in want]),
+                    q.astype(np.float32), x, rtol=RTOL)
+    # persistence: our files are readable by the oracle's reader and vice versa
+    da, db = tmp_path / "a", tmp_path / "b"
+    da.mkdir(); db.mkdir()
+    ours.serialize(str(da)); ref.serialize(str(db))
+    assert open(da / "index.faiss", "rb").read() == open(db / "index.faiss", "rb").read()
+    again = Indexer(d, 0, 8)
+    again.deserialize_from(str(db))
+    got2 = again.search_knn(q, k)
+    for (a, sa), (b, sb) in zip(got, got2):
+        assert a == b and np.array_equal(sa, sb)
+
+
+def test_indexer_rejects_pq():
+    from src.index import Indexer
+    with pytest.raises(NotImplementedError):
+        Indexer(768, 16, 8)
+
+
+def test_golden_fixture(fo):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "flatip_small.npz"))
+    e = _engine(g["corpus"])
+    for k in (1, 10, 100):
+        D, I = e.search(g["queries"], k)
+        fo.compare_topk(D, I, g[f"D_k{k}"], g[f"I_k{k}"], g["queries"], g["corpus"], rtol=RTOL)
+
+
+def test_c2_scale_subset(fo):
+    """BASELINE config 2 scale (1M x 768, k=100) on the GPU; the oracle checks a fixed random
+    subset of queries against the full corpus, every row must be descending and in range."""
+    import torch
+    n, nq, k, d = 1_000_000, 2048, 100, 768
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn((n, d), generator=gen, device="cuda")
+    x /= x.norm(dim=1, keepdim=True)
+    gen.manual_seed(4321)
+    q = torch.randn((nq, d), generator=gen, device="cuda")
+    q /= q.norm(dim=1, keepdim=True)
+    from b2ip import Engine
+    e = Engine(d, 0)
+    e.add(x)
+    D, I = e.search(q, k)
+    D, I = D.cpu().numpy(), I.cpu().numpy()
+    assert (np.diff(D, axis=1) <= 0).all() and I.min() >= 0 and I.max() < n
+    assert e.stats()["fallback_queries"] == 0
+    sel = np.random.default_rng(0).choice(nq, 64, replace=False)
+    xh, qh = x.cpu().numpy(), q[torch.from_numpy(sel).cuda()].cpu().numpy()
+    Do, Io = fo.search(qh, xh, k)
+    fo.compare_topk(D[sel], I[sel], Do, Io, qh, xh, rtol=RTOL)
