@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- exact top-k inner-product search throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2ip|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic queries: all `n_queries`
+queries against the whole row-sharded corpus (local tcgen05 scoring + fused filter + fp32
+rescore per GPU, then the NCCL all-gather + merge when N > 1).  Workload = BASELINE config 3:
+21M x 768 fp32 L2-normalised synthetic corpus, 100k queries, k = 100 (fits one B200:
+64.5 GB fp32 master + 32.3 GB bf16 shadow).  The corpus is fixed as N grows -> "strong".
+
+Prints ONE JSON line on rank 0.  `value` = queries/s with queries resident in HBM;
+`e2e` = the same through the reference-facing call with HOST buffers (H2D of the queries and
+D2H of scores+ids inside the timed region); `roofline` = the tcgen05 scoring kernel
+against the measured bf16 peak; `cpu_baseline` = the faiss-equivalent CPU oracle on the box's
+host cores on a bounded sample.  `--impl reference` times that CPU implementation alone.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # see oracle/flatip_oracle.py::_load
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "czech-contriever_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "queries/sec top-100 exact IP search, 21M x 768"
+UNIT = "queries/s"
+CHUNK = 1 << 18          # rows per generated corpus chunk (seeded by global chunk index)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b2ip", choices=["b2ip", "reference"])
+    ap.add_argument("--n-corpus", type=int, default=21_000_000)
+    ap.add_argument("--n-queries", type=int, default=100_000)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--d", type=int, default=768)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=1 << 18)
+    ap.add_argument("--cpu-sample-queries", type=int, default=4096)
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, \
+            "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU every 100 ms via NVML."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def gen_rows(torch, lo, hi, d, seed_base, device):
+    """Rows [lo,hi) of the synthetic L2-normalised Gaussian matrix; chunk c (global rows
+    [c*CHUNK,(c+1)*CHUNK)) always comes from seed seed_base*1000003+c, whatever the sharding."""
+    for c in range(lo // CHUNK, (hi + CHUNK - 1) // CHUNK):
+        c0 = c * CHUNK
+        gen = torch.Generator(device=device).manual_seed(seed_base * 1000003 + c)
+        x = torch.randn((CHUNK, d), generator=gen, device=device, dtype=torch.float32)
+        x /= x.norm(dim=1, keepdim=True)
+        a, b = max(lo, c0) - c0, min(hi, c0 + CHUNK) - c0
+        yield max(lo, c0), x[a:b]
+
+
+def cpu_reference_qps(args, sample_rows_host, sample_q_host, steps, warmup):
+    """faiss-IndexFlatIP-equivalent CPU search (oracle/flatip_oracle.c, OpenBLAS sgemm blocks +
+    reservoir handler) with all host threads, on the bounded sample; QPS is scaled to the full
+    corpus size (cost is linear in rows at fixed nq)."""
+    from oracle import flatip_oracle as fo
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        fo.search(sample_q_host, sample_rows_host, args.k)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            ts.append(dt)
+    t = sum(ts) / len(ts)
+    scale = args.n_corpus / sample_rows_host.shape[0]
+    qps = sample_q_host.shape[0] / (t * scale)
+    info = {
+        "value": qps, "unit": UNIT, "cores": fo.num_threads(), "kind": "port",
+        "sample": (f"{sample_q_host.shape[0]} queries x {sample_rows_host.shape[0]} rows of the same "
+                   f"synthetic corpus, {t:.2f} s per pass, scaled x{scale:.1f} to {args.n_corpus} rows; "
+                   f"faiss-cpu 1.8.0 not installable offline -> CPU restatement, BLAS: {fo.blas_description()}"),
+    }
+    return info, t
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (restated, see
+    oracle/), rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import numpy as np
+    rng = np.random.default_rng(1234)
+    rows = rng.standard_normal((args.cpu_sample_rows, args.d), dtype=np.float32)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    q = rng.standard_normal((args.cpu_sample_queries, args.d), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    info, t = cpu_reference_qps(args, rows, q, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": info["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * args.n_queries / info["value"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": info,
+        "e2e": {"value": info["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": (f"C3: {args.n_corpus} x {args.d} fp32 synthetic L2-normalised corpus, "
+                     f"{args.n_queries} queries, k={args.k}"),
+        "n_corpus": args.n_corpus, "n_queries": args.n_queries, "k": args.k, "d": args.d,
+        "parallelism": f"row-shard x{world} (one process per GPU, NCCL all-gather + merge)",
+        "l2": "inputs exceed L2: every step streams the whole bf16 shadow corpus (2*d bytes/row)",
+        "coarse": "tcgen05 kind::f16 bf16 operands, fp32 accumulate; fp32 rescore (fp64 accumulate)",
+    }
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world_env == 1 and "RANK" not in os.environ:
+        # convenience: relaunch under torchrun (the driver launches us that way itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from b2ip import ShardedIndex, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = world_env
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b2ip needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    N, nq, k, d = args.n_corpus, args.n_queries, args.k, args.d
+    lo, hi = shard_bounds(N, world, rank)
+    index = ShardedIndex(d, device=local_rank)
+    index.engine.reserve(hi - lo)
+    t_ing = time.perf_counter()
+    sample_host = None
+    for g0, rows in gen_rows(torch, lo, hi, d, 1234, dev):
+        index.add_local(rows, g0)
+        if rank == 0 and sample_host is None and not args.no_cpu_baseline and world == 1:
+            sample_host = rows[:min(args.cpu_sample_rows, rows.shape[0])].cpu().numpy()
+    if rank == 0 and sample_host is not None and sample_host.shape[0] < args.cpu_sample_rows:
+        extra = [sample_host]
+        need = args.cpu_sample_rows - sample_host.shape[0]
+        for g0, rows in gen_rows(torch, CHUNK, min(N, CHUNK + need), d, 1234, dev):
+            extra.append(rows.cpu().numpy())
+        sample_host = np.concatenate(extra)[:args.cpu_sample_rows]
+    torch.cuda.synchronize()
+    t_ing = time.perf_counter() - t_ing
+
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    q_dev = torch.randn((nq, d), generator=gen, device=dev, dtype=torch.float32)
+    q_dev /= q_dev.norm(dim=1, keepdim=True)
+    q_pin = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
+    q_pin.copy_(q_dev)
+    D_pin = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
+    I_pin = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+    torch.cuda.synchronize()
+    index.engine.use_torch_stream()
+
+    # ---------------------------------------------------------------- device-resident timing
+    agg = {"coarse_ms": 0.0, "coarse_flops": 0.0, "coarse_launches": 0, "launches": 0,
+           "candidates": 0, "rescored": 0, "fallback": 0, "slabs": 0}
+
+    def step_device():
+        D, I = index.search(q_dev, k)
+        st = index.engine.stats()
+        agg["coarse_ms"] += st["coarse_ms"]; agg["coarse_flops"] += st["coarse_flops"]
+        agg["coarse_launches"] += st["coarse_launches"]
+        agg["launches"] += st["total_launches"] + (1 if world > 1 else 0)
+        agg["candidates"] += st["candidates"]; agg["rescored"] += st["rescored"]
+        agg["fallback"] += st["fallback_queries"]; agg["slabs"] += st["slabs"]
+        return D, I
+
+    for _ in range(args.warmup):
+        step_device()
+    for key in agg:
+        agg[key] = 0
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        D_last, I_last = step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms / args.steps
+    value = nq / (ms_per_step / 1e3)
+
+    # ---------------------------------------------------------------- end-to-end timing
+    e2e = None
+    if not args.no_e2e:
+        def step_e2e():
+            if world == 1:
+                # the reference-facing call: host buffers across the C ABI
+                index.engine.search(q_pin.numpy(), k, out=(D_pin.numpy(), I_pin.numpy()))
+            else:
+                qd = q_pin.to(dev, non_blocking=True)
+                D, I = index.search(qd, k)
+                D_pin.copy_(D, non_blocking=True)
+                I_pin.copy_(I, non_blocking=True)
+                torch.cuda.synchronize()
+        for _ in range(max(1, args.warmup - 2)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms_e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+        e2e = {"value": nq / (ms_e / args.steps / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": world * nq * d * 4, "d2h_bytes_per_step": world * nq * k * 12,
+               "ms_per_step": ms_e / args.steps,
+               "call": "b2ip_search(mem=HOST) via ctypes" if world == 1 else "ShardedIndex.search + pinned H2D/D2H"}
+
+    # ---------------------------------------------------------------- roofline of the scoring kernel
+    peaks, peak_src = load_peaks()
+    coarse_ms = max_over_ranks(agg["coarse_ms"])
+    flops_rank = agg["coarse_flops"]
+    achieved = flops_rank / (agg["coarse_ms"] / 1e3) / 1e12 if agg["coarse_ms"] > 0 else 0.0
+    achieved = -max_over_ranks(-achieved)     # slowest rank
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak, "traffic": None,
+        "kernel": "coarse_filter_kernel<false> (tcgen05.mma kind::f16, fused threshold filter)",
+        "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a multi-second step)",
+        "burst_peak": peaks.get("bf16_tflops"),
+        "flops_per_launch_avg": flops_rank / max(1, agg["coarse_launches"]),
+        "launches": agg["coarse_launches"], "kernel_ms_per_step": coarse_ms / args.steps,
+        "kernel_share_of_step": coarse_ms / ms if ms > 0 else None,
+    }
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and sample_host is not None:
+        qs = q_dev[:args.cpu_sample_queries].cpu().numpy()
+        cpu, _ = cpu_reference_qps(args, sample_host, qs, steps=1, warmup=1)
+
+    launches = int(sum_over_ranks(agg["launches"]))
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 coarse / f32 rescore",
+            "data": "synthetic", "config": workload_config(args, world),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu,
+            "detail": {"ingest_s": t_ing, "rows_per_gpu": hi - lo,
+                       "candidates_per_query_per_step": agg["candidates"] / max(1, args.steps) / nq,
+                       "rescored_per_query_per_step": agg["rescored"] / max(1, args.steps) / nq,
+                       "fallback_queries": agg["fallback"], "slabs_per_step": agg["slabs"] / max(1, args.steps)},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

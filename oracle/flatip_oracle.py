@@ -45,6 +45,11 @@ def _load():
     global _lib
     if _lib is None:
         build()
+        # The handler loops are OpenMP, the sgemm is numpy's pthread OpenBLAS: idle OpenMP
+        # workers must sleep, not spin, or they starve the BLAS threads (measured 9.5 ->
+        # 310 GFLOP/s on 8 cores).  libgomp reads these when it is first loaded.
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+        os.environ.setdefault("GOMP_SPINCOUNT", "0")
         _lib = ctypes.CDLL(_SO)
         _lib.oracle_flatip_search.restype = ctypes.c_int
         _lib.oracle_flatip_search.argtypes = [
