@@ -52,6 +52,9 @@ class Engine:
         import torch
         self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_option(self, name: str, value: int) -> None:
+        check(self._lib.b2ip_set_option(self._h, name.encode(), int(value)), self._h)
+
     def reserve(self, n_rows: int) -> None:
         check(self._lib.b2ip_reserve(self._h, int(n_rows)), self._h)
 

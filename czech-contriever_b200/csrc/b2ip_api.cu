@@ -61,6 +61,7 @@ struct b2ip_index_s {
     b2ip_stats_t stats;
     std::string err;
     int gx = 32;
+    int hint_q = 0, hint_x = 0;           // 0 normal, 1 evict_first, 2 evict_last
     long long cand_budget_bytes = 6ll << 30;
 };
 
@@ -166,6 +167,10 @@ int make_tmap_bf16(b2ip_handle h, CUtensorMap* m, const void* base, int64_t rows
         return fail(h, B2IP_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d, rows=%lld d_pad=%d)",
                     static_cast<int>(r), static_cast<long long>(rows), d_pad);
     return B2IP_OK;
+}
+
+unsigned long long hint_policy(int v) {
+    return v == 1 ? ptx::kEvictFirst : (v == 2 ? ptx::kEvictLast : ptx::kEvictNormal);
 }
 
 cudaEvent_t get_event(b2ip_handle h, size_t i) {
@@ -291,6 +296,8 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         cp.cap = cap;
         cp.dump = nullptr;
         cp.dump_ld = 0;
+        cp.hint_q = hint_policy(h->hint_q);
+        cp.hint_x = hint_policy(h->hint_x);
 
         int64_t done = 0;
         int64_t slab = std::min<int64_t>(cap, std::max<int64_t>(1024, 8ll * k));
@@ -492,6 +499,17 @@ int b2ip_set_stream(b2ip_handle h, void* cuda_stream) {
     return B2IP_OK;
 }
 
+int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
+    if (!h || !name) return B2IP_ERR_INVALID;
+    const std::string n(name);
+    if (n == "gx") h->gx = static_cast<int>(std::max<int64_t>(1, value));
+    else if (n == "hint_q") h->hint_q = static_cast<int>(value);
+    else if (n == "hint_x") h->hint_x = static_cast<int>(value);
+    else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;
+    else return fail(h, B2IP_ERR_INVALID, "b2ip_set_option: unknown option '%s'", name);
+    return B2IP_OK;
+}
+
 int b2ip_reserve(b2ip_handle h, int64_t n_rows) {
     if (!h) return B2IP_ERR_INVALID;
     if (n_rows < 0 || n_rows >= (1ll << 32)) return fail(h, B2IP_ERR_INVALID, "n_rows=%lld out of range", (long long)n_rows);
@@ -646,6 +664,8 @@ int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev
     cp.thr = nullptr; cp.cand = nullptr; cp.cnt = nullptr; cp.cap = 0;
     cp.dump = out_dev;
     cp.dump_ld = n_rows;
+    cp.hint_q = hint_policy(h->hint_q);
+    cp.hint_x = hint_policy(h->hint_x);
     const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
     const int grid = static_cast<int>(std::min<long long>(tiles, h->sm_count));
     coarse_filter_kernel<true><<<grid, COARSE_THREADS, COARSE_SMEM_BYTES, h->stream>>>(tmap_q, tmap_x, cp);

@@ -50,6 +50,7 @@ struct CoarseParams {
     int cap;
     float* dump;             // debug: [nq, dump_ld] raw scores, or nullptr
     long long dump_ld;
+    unsigned long long hint_q, hint_x;   // L2 eviction-priority policies of the two TMA streams
 };
 
 __device__ __forceinline__ void tile_coords(const CoarseParams& p, int t, int& qt, int& xt) {
@@ -118,10 +119,9 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     ptx::tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_q, &full_bar[stage],
-                                     kb * KBLOCK_ELEMS, q_row, ptx::kEvictLast);
+                                     kb * KBLOCK_ELEMS, q_row, p.hint_q);
                     ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_x, &full_bar[stage],
-                                     kb * KBLOCK_ELEMS, static_cast<int32_t>(x_row),
-                                     ptx::kEvictNormal);
+                                     kb * KBLOCK_ELEMS, static_cast<int32_t>(x_row), p.hint_x);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }

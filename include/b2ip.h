@@ -77,6 +77,11 @@ void b2ip_destroy(b2ip_handle h);
  * stream).  Lets a torch caller keep its current stream ordering. */
 int b2ip_set_stream(b2ip_handle h, void* cuda_stream);
 
+/* Tuning knobs (all have working defaults): "gx" x-tiles per raster group, "hint_q"/"hint_x"
+ * L2 eviction priority of the query / corpus TMA streams (0 normal, 1 first, 2 last),
+ * "cand_budget_mb" device memory allowed for candidate lists (sets the query batch). */
+int b2ip_set_option(b2ip_handle h, const char* name, int64_t value);
+
 /* Optional capacity hint before a series of b2ip_add calls (avoids regrowth copies). */
 int b2ip_reserve(b2ip_handle h, int64_t n_rows);
 
