@@ -60,8 +60,9 @@ struct b2ip_index_s {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     b2ip_stats_t stats;
     std::string err;
-    int gx = 32;
+    int gx = 16;
     int hint_q = 0, hint_x = 0;           // 0 normal, 1 evict_first, 2 evict_last
+    int dbg = 0;
     long long cand_budget_bytes = 6ll << 30;
 };
 
@@ -298,6 +299,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         cp.dump_ld = 0;
         cp.hint_q = hint_policy(h->hint_q);
         cp.hint_x = hint_policy(h->hint_x);
+        cp.dbg = h->dbg;
 
         int64_t done = 0;
         int64_t slab = std::min<int64_t>(cap, std::max<int64_t>(1024, 8ll * k));
@@ -505,6 +507,7 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     if (n == "gx") h->gx = static_cast<int>(std::max<int64_t>(1, value));
     else if (n == "hint_q") h->hint_q = static_cast<int>(value);
     else if (n == "hint_x") h->hint_x = static_cast<int>(value);
+    else if (n == "dbg") h->dbg = static_cast<int>(value);
     else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;
     else return fail(h, B2IP_ERR_INVALID, "b2ip_set_option: unknown option '%s'", name);
     return B2IP_OK;

@@ -51,6 +51,8 @@ struct CoarseParams {
     float* dump;             // debug: [nq, dump_ld] raw scores, or nullptr
     long long dump_ld;
     unsigned long long hint_q, hint_x;   // L2 eviction-priority policies of the two TMA streams
+    int dbg;                 // perf experiments only (results are wrong when set):
+                             // 1 = every tile loads corpus tile 0, 2 = no TMA loads, 4 = no filter
 };
 
 __device__ __forceinline__ void tile_coords(const CoarseParams& p, int t, int& qt, int& xt) {
@@ -61,6 +63,20 @@ __device__ __forceinline__ void tile_coords(const CoarseParams& p, int t, int& q
     const int gx_eff = rem < p.gx ? rem : p.gx;
     qt = r / gx_eff;
     xt = xg * p.gx + (r - qt * gx_eff);
+}
+
+// v[j] for a run-time j without spilling v to local memory: 5-level tree of selects.
+__device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int j) {
+    uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+    return (j & 16) ? d[1] : d[0];
 }
 
 template <bool kDump>
@@ -114,9 +130,15 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 int qt, xt;
                 tile_coords(p, t, qt, xt);
                 const int q_row = qt * TILE_Q;
-                const long long x_row = p.x_row0 + static_cast<long long>(xt) * TILE_X;
+                const long long x_row =
+                    (p.dbg & 1) ? 0 : p.x_row0 + static_cast<long long>(xt) * TILE_X;
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (p.dbg & 2) {
+                        ptx::mbar_arrive(&full_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     ptx::tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_q, &full_bar[stage],
                                      kb * KBLOCK_ELEMS, q_row, p.hint_q);
@@ -175,7 +197,7 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * TILE_X);
 #pragma unroll 1
-            for (int c = 0; c < TILE_X / 32; c++) {
+            for (int c = 0; c < ((p.dbg & 4) ? 0 : TILE_X / 32); c++) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(taddr + c * 32, v);
                 ptx::tmem_ld_wait();
@@ -194,16 +216,25 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
                     for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(v[j]));
                     if (m > thr) {
-                        // rare path: at least one of this thread's 32 scores is a candidate
+                        // rare path: at least one of this thread's 32 scores is a candidate.
+                        // Branch-free hit mask, ONE counter bump for all hits of the chunk,
+                        // then only the hit columns are pulled out with a select tree.
+                        uint32_t mask = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float s = __uint_as_float(v[j]);
-                            const int col = c * 32 + j;
-                            if (s > thr && col < n_valid) {
-                                const int slot = atomicAdd(p.cnt + q, 1);
-                                if (slot < p.cap)
-                                    p.cand[static_cast<long long>(q) * p.cap + slot] =
-                                        make_key(s, static_cast<uint32_t>(x_row + col));
+                        for (int j = 0; j < 32; j++)
+                            mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+                        const int vcols = n_valid - c * 32;          // columns of this chunk in range
+                        if (vcols < 32) mask &= vcols > 0 ? ((1u << vcols) - 1u) : 0u;
+                        if (mask) {
+                            int slot = atomicAdd(p.cnt + q, __popc(mask));
+                            unsigned long long* dst = p.cand + static_cast<long long>(q) * p.cap;
+                            const uint32_t row0 = static_cast<uint32_t>(x_row) + c * 32;
+                            while (mask) {
+                                const int j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const uint32_t bits = select32(v, j);
+                                if (slot < p.cap) dst[slot] = make_key(__uint_as_float(bits), row0 + j);
+                                slot++;
                             }
                         }
                     }
