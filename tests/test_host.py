@@ -1,0 +1,223 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/b2ip.h
+declares (no compute without a GPU -- creation must fail loudly, not fall back), the
+index.faiss reader/writer, the key ordering shared by all selection kernels, and the
+row-sharded search plumbing under a world_size-2 gloo group."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cuda_available():
+    import torch
+    return torch.cuda.is_available()
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    import b2ip
+    return b2ip
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "b2ip.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b2ip_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(built.SYMBOLS), declared ^ set(built.SYMBOLS)
+    lib = built.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", built.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (b2ip_[a-z_0-9]+)", out))
+    assert declared <= exported
+
+
+def test_library_is_sm100a_tcgen05_code(built):
+    """The shipped kernels are Blackwell-native: tcgen05 MMA, TMA and TMEM loads in the SASS."""
+    sass = subprocess.run(["cuobjdump", "-sass", built.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+@pytest.mark.skipif(_cuda_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_means_loud_failure_not_cpu_fallback(built):
+    with pytest.raises(built.B2ipError) as ei:
+        built.Engine(768, 0)
+    assert "no CPU fallback" in str(ei.value)
+    from src.index import Indexer
+    with pytest.raises(built.B2ipError):
+        Indexer(768, 0, 8)
+
+
+def test_indexer_rejects_pq_without_touching_the_gpu(built):
+    from src.index import Indexer
+    with pytest.raises(NotImplementedError):
+        Indexer(768, 16, 8)
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "czech-contriever_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_index_faiss_format_round_trip(tmp_path, built):
+    from oracle import flatip_oracle as fo
+    rows = synth(1000, 24, 3)
+    ours, theirs = str(tmp_path / "ours.faiss"), str(tmp_path / "theirs.faiss")
+    built.write_flat_ip(ours, 24, 1000, lambda r0, n: rows[r0:r0 + n])
+    fo.write_index_flat_ip(theirs, rows)
+    raw = open(ours, "rb").read()
+    assert raw == open(theirs, "rb").read()
+    assert raw[:4] == b"IxFI" and len(raw) == 45 + 4 * 1000 * 24
+    d, n, blocks = built.stream_flat_ip_rows(theirs)
+    assert (d, n) == (24, 1000)
+    assert np.array_equal(np.concatenate(list(blocks)), rows)
+    assert np.array_equal(fo.read_index_flat_ip(ours), rows)
+
+
+def test_index_faiss_rejects_other_index_types(tmp_path, built):
+    p = tmp_path / "pq.faiss"
+    p.write_bytes(b"IxPq" + b"\0" * 64)
+    with pytest.raises(NotImplementedError):
+        built.stream_flat_ip_rows(str(p))
+    q = tmp_path / "short.faiss"
+    q.write_bytes(b"IxFI\0\0")
+    with pytest.raises(ValueError):
+        built.stream_flat_ip_rows(str(q))
+
+
+def test_shard_bounds_partition_rows(built):
+    for n in (0, 1, 7, 100, 21_000_000, 21_015_324):
+        for g in (1, 2, 3, 4, 8):
+            spans = [built.shard_bounds(n, g, r) for r in range(g)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) <= -(-n // g)
+
+
+def test_key_ordering_host_build(tmp_path):
+    """keys.cuh compiled for the host: larger key <=> (higher score, then lower row); NaN -> 0."""
+    src = tmp_path / "k.cu"
+    src.write_text(r'''
+#include <cstdio>
+#include <cmath>
+#include <vector>
+#include "keys.cuh"
+using namespace b2ip;
+int main() {
+    std::vector<float> v = {-INFINITY, -3.4e38f, -1.f, -1e-30f, -0.f, 0.f, 1e-30f, 0.5f, 1.f, 3.4e38f, INFINITY};
+    for (size_t i = 0; i + 1 < v.size(); i++) {
+        if (!(order_f32(v[i]) <= order_f32(v[i + 1]))) { printf("order %zu\n", i); return 1; }
+        if (v[i] < v[i + 1] && !(make_key(v[i], 0) < make_key(v[i + 1], 4000000000u))) return 2;
+        if (unorder_f32(order_f32(v[i])) != v[i]) return 3;
+    }
+    if (order_f32(NAN) != 0u || order_f32(-INFINITY) == 0u) return 4;
+    if (!(make_key(1.f, 5) > make_key(1.f, 6))) return 5;          // tie -> lower row wins
+    if (key_row(make_key(2.f, 123456789u)) != 123456789u || key_score(make_key(2.f, 1)) != 2.f) return 6;
+    printf("ok\n");
+    return 0;
+}''')
+    exe = tmp_path / "k"
+    inc = os.path.join(ROOT, "czech-contriever_b200", "csrc")
+    subprocess.run(["nvcc", "-O1", "-I", inc, "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, (out.returncode, out.stdout)
+
+
+# ------------------------------------------------------------------------------------------
+# row-sharded search under gloo, world_size 2 (the NCCL path minus the GPU): the engine and
+# the merge are replaced by CPU stand-ins built on the oracle, everything else is product code
+# ------------------------------------------------------------------------------------------
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path[:0] = [ROOT, os.path.join(ROOT, "czech-contriever_b200"), os.path.join(ROOT, "tests")]
+from oracle import flatip_oracle as fo
+from b2ip.sharded import ShardedIndex
+from helpers import synth
+
+class OracleEngine:                      # CPU stand-in for b2ip.Engine (tests only)
+    def __init__(self, d): self.rows = np.empty((0, d), np.float32)
+    def add(self, rows): self.rows = np.concatenate([self.rows, np.asarray(rows, np.float32)])
+    def search(self, q, k, mode="auto"):
+        D, I = fo.search(q.numpy(), self.rows, k)
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+def merge(gD, gI, k):                    # CPU stand-in for the merge kernel: score desc, row asc
+    G, nq, _ = gD.shape
+    D = gD.permute(1, 0, 2).reshape(nq, G * k).numpy(); I = gI.permute(1, 0, 2).reshape(nq, G * k).numpy()
+    D = np.where(I >= 0, D, -np.inf)
+    order = np.lexsort((np.where(I >= 0, I, 1 << 62), -D), axis=1)[:, :k]
+    Dm, Im = np.take_along_axis(D, order, 1), np.take_along_axis(I, order, 1)
+    Dm = np.where(Im >= 0, Dm, np.finfo(np.float32).min).astype(np.float32)
+    return torch.from_numpy(Dm), torch.from_numpy(Im)
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["MASTER_PORT"], rank=rank, world_size=world)
+d, k = 48, 20
+x, q = synth(5000, d, 1234), synth(37, d, 4321)
+x[3000:3010] = x[10:20]                  # exact ties across the two shards
+idx = ShardedIndex(d, engine=OracleEngine(d), merge_fn=merge)
+for a, b in [(0, 900), (900, 2000), (2000, 2001), (2001, 4200), (4200, 5000)]:
+    idx.add_replicated(x[a:b])           # SPMD ingest: chunk i kept by rank i % world
+assert idx.ntotal_local == sum(b - a for i, (a, b) in enumerate([(0, 900), (900, 2000), (2000, 2001), (2001, 4200), (4200, 5000)]) if i % world == rank)
+D, I = idx.search(torch.from_numpy(q), k)
+D64, I64 = fo.brute_force_f64(q, x, k)
+fo.compare_topk(D.numpy(), I.numpy(), D64.astype(np.float32), I64, q, x, rtol=1e-5)
+assert np.array_equal(I.numpy(), I64), "ties must resolve to the lower GLOBAL row"
+# contiguous sharding through add_local + shard_bounds gives the same answer
+from b2ip.sharded import shard_bounds
+idx2 = ShardedIndex(d, engine=OracleEngine(d), merge_fn=merge)
+lo, hi = shard_bounds(5000, world, rank)
+idx2.add_local(x[lo:hi], lo)
+D2, I2 = idx2.search(torch.from_numpy(q), k)
+assert np.array_equal(I2.numpy(), I64)
+# k larger than one shard's rows: -1 padding must survive the merge
+idx3 = ShardedIndex(d, engine=OracleEngine(d), merge_fn=merge)
+idx3.add_local(x[rank * 3:(rank + 1) * 3], rank * 3)
+D3, I3 = idx3.search(torch.from_numpy(q[:4]), 10)
+assert (np.sort(I3.numpy()[:, :6], axis=1) == np.arange(6)).all() and (I3.numpy()[:, 6:] == -1).all()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_sharded_search_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(f"ROOT = {ROOT!r}\n" + _WORKER)
+    port = str(29000 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port,
+                   OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"rank {r} ok" in o, o[-3000:]
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--cpu-sample-rows", "20000", "--cpu-sample-queries", "64"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("C3")
