@@ -12,14 +12,15 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libb2ip.so")
 
 B2IP_OK = 0
-B2IP_F32, B2IP_F16 = 0, 1
+B2IP_F32, B2IP_F16, B2IP_BF16 = 0, 1, 2
+STORE_F32, STORE_BF16 = 0, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 MODE_AUTO, MODE_TENSOR, MODE_EXACT = 0, 1, 2
 MAX_K = 2048
 
 # every symbol include/b2ip.h declares (tests check the .so exports all of them)
 SYMBOLS = (
-    "b2ip_create", "b2ip_destroy", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_ntotal",
+    "b2ip_create", "b2ip_create_ex", "b2ip_destroy", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_ntotal",
     "b2ip_dim", "b2ip_set_row_offset", "b2ip_search", "b2ip_merge_topk", "b2ip_export_rows",
     "b2ip_stats", "b2ip_last_error", "b2ip_debug_coarse_scores", "b2ip_version",
 )
@@ -63,6 +64,7 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
     lib.b2ip_create.argtypes = [i32, i32, ctypes.POINTER(vp)]
+    lib.b2ip_create_ex.argtypes = [i32, i32, i32, ctypes.POINTER(vp)]
     lib.b2ip_destroy.argtypes = [vp]
     lib.b2ip_destroy.restype = None
     lib.b2ip_set_stream.argtypes = [vp, vp]
@@ -81,7 +83,7 @@ def load() -> ctypes.CDLL:
     lib.b2ip_last_error.restype = ctypes.c_char_p
     lib.b2ip_debug_coarse_scores.argtypes = [vp, i64, vp, i64, i64, vp]
     lib.b2ip_version.restype = ctypes.c_char_p
-    for name in ("b2ip_create", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_dim",
+    for name in ("b2ip_create", "b2ip_create_ex", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_dim",
                  "b2ip_set_row_offset", "b2ip_search", "b2ip_merge_topk", "b2ip_export_rows",
                  "b2ip_stats", "b2ip_debug_coarse_scores"):
         getattr(lib, name).restype = i32

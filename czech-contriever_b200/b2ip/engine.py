@@ -13,8 +13,8 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (B2IP_F16, B2IP_F32, MEM_DEVICE, MEM_HOST, MODE_AUTO, MODE_EXACT, MODE_TENSOR,
-                   B2ipError, Stats, check)
+from ._lib import (B2IP_BF16, B2IP_F16, B2IP_F32, MEM_DEVICE, MEM_HOST, MODE_AUTO, MODE_EXACT,
+                   MODE_TENSOR, STORE_BF16, STORE_F32, B2ipError, Stats, check)
 
 _MODES = {"auto": MODE_AUTO, "tensor": MODE_TENSOR, "exact": MODE_EXACT}
 
@@ -24,10 +24,15 @@ def _is_torch(x) -> bool:
 
 
 class Engine:
-    def __init__(self, d: int, device: int = 0):
+    def __init__(self, d: int, device: int = 0, store: str = "f32"):
+        """store="f32": fp32 master rows (faiss semantics).  store="bf16": the index keeps rows in
+        bf16 only (rounded at ingest unless handed in as bf16) and is exact w.r.t. those values
+        with an fp32 rescore -- BASELINE config 4, half the HBM."""
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
-        check(self._lib.b2ip_create(int(d), int(device), ctypes.byref(self._h)), None)
+        self.store = store
+        st = {"f32": STORE_F32, "bf16": STORE_BF16}[store]
+        check(self._lib.b2ip_create_ex(int(d), int(device), st, ctypes.byref(self._h)), None)
         self.d = int(d)
         self.device = int(device)
 
@@ -72,12 +77,13 @@ class Engine:
         if _is_torch(rows):
             import torch
             assert rows.is_cuda and rows.device.index == self.device, "tensor must live on the engine's GPU"
-            if rows.dtype not in (torch.float16, torch.float32):
+            ok = (torch.float16, torch.float32) + ((torch.bfloat16,) if self.store == "bf16" else ())
+            if rows.dtype not in ok:
                 rows = rows.float()
             rows = rows.contiguous()
             assert rows.dim() == 2 and rows.shape[1] == self.d, tuple(rows.shape)
             torch.cuda.current_stream(self.device).synchronize()
-            dt = B2IP_F16 if rows.dtype == torch.float16 else B2IP_F32
+            dt = {torch.float16: B2IP_F16, torch.float32: B2IP_F32, torch.bfloat16: B2IP_BF16}[rows.dtype]
             check(self._lib.b2ip_add(self._h, rows.shape[0], ctypes.c_void_p(rows.data_ptr()), dt,
                                      MEM_DEVICE), self._h)
             return

@@ -20,7 +20,7 @@ def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
 
 class ShardedIndex:
     def __init__(self, d: int, device: Optional[int] = None, engine=None, group=None,
-                 merge_fn: Optional[Callable] = None):
+                 merge_fn: Optional[Callable] = None, store: str = "f32"):
         import torch
         import torch.distributed as dist
         self._torch, self._dist = torch, dist
@@ -33,7 +33,7 @@ class ShardedIndex:
             from .engine import Engine, merge_topk
             if device is None:
                 device = torch.cuda.current_device()
-            engine = Engine(d, device)
+            engine = Engine(d, device, store=store)
             merge_fn = merge_fn or merge_topk
         self.engine = engine
         self.merge_fn = merge_fn

@@ -49,6 +49,7 @@ struct b2ip_index_s {
     float* x32 = nullptr;
     __nv_bfloat16* x16 = nullptr;
     int64_t n = 0, cap_rows = 0, row_offset = 0;
+    bool store_bf16 = false;              // rows ARE bf16: no fp32 master
     unsigned int* norm_stats = nullptr;   // device [2]
     long long* gstats = nullptr;          // device [GS_COUNT]
     long long* h_gstats = nullptr;        // pinned host mirror
@@ -63,6 +64,7 @@ struct b2ip_index_s {
     int gx = 16;
     int hint_q = 0, hint_x = 0;           // 0 normal, 1 evict_first, 2 evict_last
     int dbg = 0;
+    int verbose = 0;
     long long cand_budget_bytes = 6ll << 30;
 };
 
@@ -122,15 +124,19 @@ int grow_rows(b2ip_handle h, int64_t need, bool exact = false) {
     if (!exact) ncap = std::max<int64_t>(std::max<int64_t>(need, h->cap_rows + h->cap_rows / 2), 4096);
     float* nx32 = nullptr;
     __nv_bfloat16* nx16 = nullptr;
-    cudaError_t e = cudaMalloc(&nx32, static_cast<size_t>(ncap) * h->d * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&nx16, static_cast<size_t>(ncap) * h->d_pad * 2);
+    auto alloc_both = [&](int64_t rows) {
+        cudaError_t e = cudaSuccess;
+        if (!h->store_bf16) e = cudaMalloc(&nx32, static_cast<size_t>(rows) * h->d * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&nx16, static_cast<size_t>(rows) * h->d_pad * 2);
+        return e;
+    };
+    cudaError_t e = alloc_both(ncap);
     if (e != cudaSuccess && ncap > need) {   // retry with the exact size
         cudaGetLastError();
         if (nx32) cudaFree(nx32);
         nx32 = nullptr; nx16 = nullptr;
         ncap = need;
-        e = cudaMalloc(&nx32, static_cast<size_t>(ncap) * h->d * sizeof(float));
-        if (e == cudaSuccess) e = cudaMalloc(&nx16, static_cast<size_t>(ncap) * h->d_pad * 2);
+        e = alloc_both(ncap);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -140,8 +146,9 @@ int grow_rows(b2ip_handle h, int64_t need, bool exact = false) {
                     static_cast<long long>(ncap), cudaGetErrorString(e));
     }
     if (h->n > 0) {
-        CU_TRY(h, cudaMemcpyAsync(nx32, h->x32, static_cast<size_t>(h->n) * h->d * sizeof(float),
-                                  cudaMemcpyDeviceToDevice, h->stream));
+        if (!h->store_bf16)
+            CU_TRY(h, cudaMemcpyAsync(nx32, h->x32, static_cast<size_t>(h->n) * h->d * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, h->stream));
         CU_TRY(h, cudaMemcpyAsync(nx16, h->x16, static_cast<size_t>(h->n) * h->d_pad * 2,
                                   cudaMemcpyDeviceToDevice, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -219,7 +226,8 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
     for (int64_t g0 = 0; g0 < nql; g0 += EXACT_QB) {
         const int nqg = static_cast<int>(std::min<int64_t>(EXACT_QB, nql - g0));
         exact_scores_kernel<<<std::max(sgrid, 1), 256, sq_bytes, h->stream>>>(
-            h->x32, n, h->d, q32, qlist_dev + g0, nqg, reinterpret_cast<float*>(h->exact_scores.p));
+            h->x32, h->x16, n, h->d, h->d_pad, q32, qlist_dev + g0, nqg,
+            reinterpret_cast<float*>(h->exact_scores.p));
         exact_init_kernel<<<1, 256, 0, h->stream>>>(st, ghist, gcnt, k);
         for (int pass = 0; pass < 8; pass++) {
             exact_hist_kernel<<<dim3(std::max(hgrid, 1), nqg), 256, 0, h->stream>>>(
@@ -234,6 +242,7 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
         fp.qlist = qlist_dev + g0;
         fp.cand = reinterpret_cast<unsigned long long*>(h->cand.p);
         fp.cnt = gcnt; fp.flags = nullptr; fp.q32 = q32; fp.x32 = h->x32;
+        fp.x16 = h->x16; fp.d_pad = h->d_pad;
         fp.row_offset = h->row_offset;
         fp.out_scores = d_scores; fp.out_rows = reinterpret_cast<long long*>(d_rows);
         fp.gstats = nullptr;
@@ -334,6 +343,13 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             done += s;
             const long long m_max = std::max<long long>(h->h_gstats[GS_MAX_KEPT], 1);
             overflowed = h->h_gstats[GS_OVERFLOW];
+            if (h->verbose) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                fprintf(stderr, "[b2ip] slab rows [%lld,+%lld) %.3f ms %.0f TFLOP/s  max_kept=%lld cand_total=%lld overflow=%lld\n",
+                        (long long)(done - s), (long long)s, ms, 2.0 * nqb * (double)s * h->d / ms / 1e9,
+                        m_max, (long long)h->h_gstats[GS_CANDIDATES], overflowed);
+            }
             // next slab: expected new hits per query ~ m_max * slab / done; keep the list
             // below ~70 % of its capacity so Poisson noise does not overflow it.
             const double room = 0.70 * cap - static_cast<double>(m_max);
@@ -351,6 +367,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         fp.cnt = reinterpret_cast<int*>(h->kept.p);
         fp.flags = reinterpret_cast<int*>(h->flags.p);
         fp.q32 = qptr; fp.x32 = h->x32;
+        fp.x16 = h->x16; fp.d_pad = h->d_pad;
         fp.row_offset = h->row_offset;
         fp.out_scores = d_scores + q0 * k;
         fp.out_rows = reinterpret_cast<long long*>(d_rows) + q0 * k;
@@ -422,8 +439,14 @@ extern "C" {
 const char* b2ip_version(void) { return "b2ip 0.1 sm_100a (tcgen05 bf16 coarse + fp32 rescore)"; }
 
 int b2ip_create(int d, int device, b2ip_handle* out) {
+    return b2ip_create_ex(d, device, B2IP_STORE_F32, out);
+}
+
+int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     if (!out) return fail(nullptr, B2IP_ERR_INVALID, "out is NULL");
     *out = nullptr;
+    if (store_dtype != B2IP_STORE_F32 && store_dtype != B2IP_STORE_BF16)
+        return fail(nullptr, B2IP_ERR_INVALID, "store_dtype=%d: use B2IP_STORE_F32 or B2IP_STORE_BF16", store_dtype);
     if (d <= 0 || d % 4 != 0 || d > 4096)
         return fail(nullptr, B2IP_ERR_INVALID, "d=%d: dimension must be a multiple of 4 in [4,4096]", d);
     int ndev = 0;
@@ -444,6 +467,7 @@ int b2ip_create(int d, int device, b2ip_handle* out) {
                     prop.major, prop.minor);
     b2ip_handle h = new b2ip_index_s();
     h->d = d;
+    h->store_bf16 = store_dtype == B2IP_STORE_BF16;
     h->d_pad = (d + KBLOCK_ELEMS - 1) / KBLOCK_ELEMS * KBLOCK_ELEMS;
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
@@ -508,6 +532,7 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "hint_q") h->hint_q = static_cast<int>(value);
     else if (n == "hint_x") h->hint_x = static_cast<int>(value);
     else if (n == "dbg") h->dbg = static_cast<int>(value);
+    else if (n == "verbose") h->verbose = static_cast<int>(value);
     else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;
     else return fail(h, B2IP_ERR_INVALID, "b2ip_set_option: unknown option '%s'", name);
     return B2IP_OK;
@@ -524,30 +549,63 @@ int b2ip_reserve(b2ip_handle h, int64_t n_rows) {
 int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem) {
     if (!h) return B2IP_ERR_INVALID;
     if (n < 0 || (n > 0 && !rows)) return fail(h, B2IP_ERR_INVALID, "b2ip_add: bad rows pointer / n=%lld", (long long)n);
-    if (src_dtype != B2IP_F32 && src_dtype != B2IP_F16) return fail(h, B2IP_ERR_INVALID, "b2ip_add: src_dtype=%d", src_dtype);
+    if (src_dtype != B2IP_F32 && src_dtype != B2IP_F16 && src_dtype != B2IP_BF16)
+        return fail(h, B2IP_ERR_INVALID, "b2ip_add: src_dtype=%d", src_dtype);
     if (mem != B2IP_MEM_HOST && mem != B2IP_MEM_DEVICE) return fail(h, B2IP_ERR_INVALID, "b2ip_add: mem=%d", mem);
+    if (src_dtype == B2IP_BF16 && !h->store_bf16)
+        return fail(h, B2IP_ERR_INVALID, "b2ip_add: bf16 rows need an index created with B2IP_STORE_BF16");
     if (n == 0) return B2IP_OK;
     if (h->n + n >= (1ll << 32) - 1) return fail(h, B2IP_ERR_UNSUPPORTED, "a shard holds at most 2^32-2 rows");
     Guard g(h->device);
     RC_TRY(grow_rows(h, h->n + n));
-    float* dst = h->x32 + h->n * h->d;
-    const size_t count = static_cast<size_t>(n) * h->d;
     const cudaMemcpyKind kind = mem == B2IP_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-    if (src_dtype == B2IP_F32) {
-        CU_TRY(h, cudaMemcpyAsync(dst, rows, count * sizeof(float), kind, h->stream));
-    } else {
-        const __half* src = static_cast<const __half*>(rows);
-        if (mem == B2IP_MEM_HOST) {
-            RC_TRY(ensure(h, h->stage, count * sizeof(__half)));
-            CU_TRY(h, cudaMemcpyAsync(h->stage.p, rows, count * sizeof(__half), kind, h->stream));
-            src = static_cast<const __half*>(h->stage.p);
+    const int rgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 16));
+    // bf16 storage ingests in bounded chunks through a staging buffer (there is no fp32 master)
+    const int64_t chunk = h->store_bf16 ? std::min<int64_t>(n, 1 << 18) : n;
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        const int64_t cn = std::min<int64_t>(chunk, n - c0);
+        const size_t count = static_cast<size_t>(cn) * h->d;
+        const int64_t r0 = h->n + c0;
+        if (src_dtype == B2IP_BF16) {
+            const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(rows) + static_cast<size_t>(c0) * h->d;
+            if (mem == B2IP_MEM_HOST) {
+                RC_TRY(ensure(h, h->stage, count * 2));
+                CU_TRY(h, cudaMemcpyAsync(h->stage.p, src, count * 2, kind, h->stream));
+                src = static_cast<const __nv_bfloat16*>(h->stage.p);
+            }
+            ingest_bf16_rows_kernel<<<rgrid, 256, 0, h->stream>>>(src, h->x16, r0, r0 + cn, h->d, h->d_pad,
+                                                                  h->norm_stats);
+            continue;
         }
-        const int grid = static_cast<int>(std::min<size_t>((count / 2 + 255) / 256 + 1, 65535));
-        widen_f16_kernel<<<grid, 256, 0, h->stream>>>(src, dst, static_cast<long long>(count));
+        // fp32 destination of this chunk: the master rows, or a staging area (bf16 storage)
+        float* dst32;
+        size_t f16_off = 0;
+        if (h->store_bf16) {
+            f16_off = count * sizeof(float);
+            RC_TRY(ensure(h, h->stage, f16_off + (src_dtype == B2IP_F16 && mem == B2IP_MEM_HOST ? count * 2 : 0)));
+            dst32 = static_cast<float*>(h->stage.p);
+        } else {
+            dst32 = h->x32 + r0 * h->d;
+            if (src_dtype == B2IP_F16 && mem == B2IP_MEM_HOST) RC_TRY(ensure(h, h->stage, count * 2));
+        }
+        if (src_dtype == B2IP_F32) {
+            const float* src = static_cast<const float*>(rows) + static_cast<size_t>(c0) * h->d;
+            if (h->store_bf16 && mem == B2IP_MEM_DEVICE) dst32 = const_cast<float*>(src);   // convert in place from the caller's buffer
+            else CU_TRY(h, cudaMemcpyAsync(dst32, src, count * sizeof(float), kind, h->stream));
+        } else {
+            const __half* src = static_cast<const __half*>(rows) + static_cast<size_t>(c0) * h->d;
+            if (mem == B2IP_MEM_HOST) {
+                __half* st = reinterpret_cast<__half*>(static_cast<char*>(h->stage.p) + f16_off);
+                CU_TRY(h, cudaMemcpyAsync(st, src, count * 2, kind, h->stream));
+                src = st;
+            }
+            const int grid = static_cast<int>(std::min<size_t>((count / 2 + 255) / 256 + 1, 65535));
+            widen_f16_kernel<<<grid, 256, 0, h->stream>>>(src, dst32, static_cast<long long>(count));
+        }
+        shadow_rows_kernel<<<rgrid, 256, 0, h->stream>>>(dst32, r0, h->x16, r0, r0 + cn, h->d, h->d_pad,
+                                                         h->norm_stats, !h->store_bf16);
+        if (h->store_bf16) CU_TRY(h, cudaStreamSynchronize(h->stream));   // staging buffer is reused
     }
-    const int grid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 16));
-    shadow_rows_kernel<<<grid, 256, 0, h->stream>>>(h->x32, h->x16, h->n, h->n + n, h->d, h->d_pad,
-                                                    h->norm_stats);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     h->n += n;
@@ -621,7 +679,18 @@ int b2ip_export_rows(b2ip_handle h, int64_t row0, int64_t n, float* out, int mem
         return fail(h, B2IP_ERR_INVALID, "b2ip_export_rows: [%lld,+%lld) outside [0,%lld)", (long long)row0, (long long)n, (long long)h->n);
     if (n == 0) return B2IP_OK;
     Guard g(h->device);
-    CU_TRY(h, cudaMemcpyAsync(out, h->x32 + row0 * h->d, static_cast<size_t>(n) * h->d * sizeof(float),
+    const float* src = h->x32 ? h->x32 + row0 * h->d : nullptr;
+    if (h->store_bf16) {
+        float* tmp = out;
+        if (mem == B2IP_MEM_HOST) {
+            RC_TRY(ensure(h, h->stage, static_cast<size_t>(n) * h->d * sizeof(float)));
+            tmp = static_cast<float*>(h->stage.p);
+        }
+        widen_bf16_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(h->x16, row0, n, h->d, h->d_pad, tmp);
+        if (mem == B2IP_MEM_DEVICE) { CU_TRY(h, cudaStreamSynchronize(h->stream)); return B2IP_OK; }
+        src = tmp;
+    }
+    CU_TRY(h, cudaMemcpyAsync(out, src, static_cast<size_t>(n) * h->d * sizeof(float),
                               mem == B2IP_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return B2IP_OK;

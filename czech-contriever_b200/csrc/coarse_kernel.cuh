@@ -32,7 +32,10 @@ constexpr int A_STAGE_BYTES = TILE_Q * KBLOCK_BYTES;   // 16 KiB
 constexpr int B_STAGE_BYTES = TILE_X * KBLOCK_BYTES;   // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int COARSE_THREADS = 256;
-constexpr int COARSE_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int HIT_SLOTS = 8;         // per-thread staging slots for filter hits (shared memory)
+constexpr int HIT_STAGE_BYTES = HIT_SLOTS * 128 * 8;
+constexpr int COARSE_SMEM_BYTES =
+    STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + HIT_STAGE_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t IDESC_BF16 = ptx::umma_idesc(/*bf16*/ 1, TILE_Q, TILE_X);
 
@@ -79,6 +82,15 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int j) {
     return (j & 16) ? d[1] : d[0];
 }
 
+// Appends a thread's staged hits to its query's candidate list: ONE counter bump per flush.
+__device__ __forceinline__ void flush_hits(const CoarseParams& p, int q,
+                                           const unsigned long long* my_stage, int n) {
+    const int slot = atomicAdd(p.cnt + q, n);
+    unsigned long long* dst = p.cand + static_cast<long long>(q) * p.cap;
+    for (int i = 0; i < n; i++)
+        if (slot + i < p.cap) dst[slot + i] = my_stage[i * 128];
+}
+
 template <bool kDump>
 __global__ void __launch_bounds__(COARSE_THREADS, 1)
 coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -95,6 +107,9 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
     uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    // hit staging: slot i of epilogue thread e lives at hit_stage[i * 128 + e] (conflict-free)
+    unsigned long long* hit_stage =
+        reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -186,6 +201,8 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
             int qt, xt;
             tile_coords(p, t, qt, xt);
             const int q = qt * TILE_Q + wq * 32 + lane;
+            unsigned long long* my_stage = hit_stage + (wq * 32 + lane);
+            int n_staged = 0;
             const long long x_row = p.x_row0 + static_cast<long long>(xt) * TILE_X;
             const long long left = p.x_row_end - x_row;
             const int n_valid = left < TILE_X ? static_cast<int>(left) : TILE_X;
@@ -225,10 +242,12 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                             mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
                         const int vcols = n_valid - c * 32;          // columns of this chunk in range
                         if (vcols < 32) mask &= vcols > 0 ? ((1u << vcols) - 1u) : 0u;
-                        if (mask) {
-                            int slot = atomicAdd(p.cnt + q, __popc(mask));
+                        const uint32_t row0 = static_cast<uint32_t>(x_row) + c * 32;
+                        const int nh = __popc(mask);
+                        if (n_staged + nh > HIT_SLOTS) {
+                            // dense chunk (early slabs): append straight from registers
+                            int slot = atomicAdd(p.cnt + q, nh);
                             unsigned long long* dst = p.cand + static_cast<long long>(q) * p.cap;
-                            const uint32_t row0 = static_cast<uint32_t>(x_row) + c * 32;
                             while (mask) {
                                 const int j = __ffs(mask) - 1;
                                 mask &= mask - 1;
@@ -236,13 +255,26 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                 if (slot < p.cap) dst[slot] = make_key(__uint_as_float(bits), row0 + j);
                                 slot++;
                             }
+                        } else {
+                            // sparse chunk (the bulk of the work): stage in shared memory, the
+                            // global append happens once per tile after the accumulator is released
+                            while (mask) {
+                                const int j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const uint32_t bits = select32(v, j);
+                                my_stage[n_staged * 128] = make_key(__uint_as_float(bits), row0 + j);
+                                n_staged++;
+                            }
                         }
                     }
                 }
             }
+            // hand the accumulator back before touching global memory: the (latency-bound)
+            // counter bump + key stores then overlap the MMAs of the following tiles
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
+            if (!kDump && n_staged) flush_hits(p, q, my_stage, n_staged);
         }
     }
 

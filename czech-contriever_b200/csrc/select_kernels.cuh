@@ -49,24 +49,29 @@ __global__ void widen_f16_kernel(const __half* __restrict__ src, float* __restri
 
 // One warp per row: bf16 shadow (zero padded to d_pad) + max ||x||^2 and max ||x - bf16(x)||^2
 // over all rows, which feed the per-query error bound of the coarse scores.
-__global__ void shadow_rows_kernel(const float* __restrict__ x32, __nv_bfloat16* __restrict__ x16,
+// `src` points at the fp32 rows of [row0,row1) (src_row0 = index of its first row): the master
+// rows themselves (fp32 storage) or a staging chunk (bf16 storage, count_delta = false: the
+// stored value IS the bf16 one, so x - bf(x) is zero by definition).
+__global__ void shadow_rows_kernel(const float* __restrict__ src, long long src_row0,
+                                   __nv_bfloat16* __restrict__ x16,
                                    long long row0, long long row1, int d, int d_pad,
-                                   unsigned int* __restrict__ norm_stats) {
+                                   unsigned int* __restrict__ norm_stats, bool count_delta) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     float mx = 0.f, md = 0.f;
     for (long long r = row0 + warp; r < row1; r += nwarps) {
-        const float4* src = reinterpret_cast<const float4*>(x32 + r * d);
+        const float4* srow = reinterpret_cast<const float4*>(src + (r - src_row0) * d);
         uint2* dst = reinterpret_cast<uint2*>(x16 + r * d_pad);
         float nx = 0.f, nd = 0.f;
         for (int j = lane; j < d_pad / 4; j += 32) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < d / 4) v = __ldg(src + j);
+            if (j < d / 4) v = __ldg(srow + j);
             const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
             const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
             const float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);
             const float e0 = v.x - flo.x, e1 = v.y - flo.y, e2 = v.z - fhi.x, e3 = v.w - fhi.y;
+            if (!count_delta) v = make_float4(flo.x, flo.y, fhi.x, fhi.y);
             nx += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
             nd += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
             uint2 o;
@@ -77,13 +82,61 @@ __global__ void shadow_rows_kernel(const float* __restrict__ x32, __nv_bfloat16*
         nx = warp_sum(nx);
         nd = warp_sum(nd);
         if (nx == nx) mx = fmaxf(mx, nx);   // NaN rows never score, keep them out of the bound
-        if (nd == nd) md = fmaxf(md, nd);
+        if (nd == nd && count_delta) md = fmaxf(md, nd);
     }
     if (lane == 0) {
         // non-negative floats order like their bit patterns
         atomicMax(norm_stats + 0, __float_as_uint(mx));
         atomicMax(norm_stats + 1, __float_as_uint(md));
     }
+}
+
+// bf16 rows handed in as bf16: copy into the padded layout + max ||x||^2.  One warp per row.
+__global__ void ingest_bf16_rows_kernel(const __nv_bfloat16* __restrict__ src,
+                                        __nv_bfloat16* __restrict__ x16, long long row0,
+                                        long long row1, int d, int d_pad,
+                                        unsigned int* __restrict__ norm_stats) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    float mx = 0.f;
+    for (long long r = row0 + warp; r < row1; r += nwarps) {
+        const __nv_bfloat162* srow = reinterpret_cast<const __nv_bfloat162*>(src + (r - row0) * d);
+        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(x16 + r * d_pad);
+        float nx = 0.f;
+        for (int j = lane; j < d_pad / 2; j += 32) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+            if (j < d / 2) v = srow[j];
+            const float2 f = __bfloat1622float2(v);
+            nx += f.x * f.x + f.y * f.y;
+            dst[j] = v;
+        }
+        nx = warp_sum(nx);
+        if (nx == nx) mx = fmaxf(mx, nx);
+    }
+    if (lane == 0) atomicMax(norm_stats + 0, __float_as_uint(mx));
+}
+
+__global__ void widen_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x16, long long row0,
+                                       long long n, int d, int d_pad, float* __restrict__ out) {
+    const long long total = n * d;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / d;
+        const int j = static_cast<int>(i - r * d);
+        out[i] = __bfloat162float(x16[(row0 + r) * d_pad + j]);
+    }
+}
+
+// One corpus row as 4 consecutive floats starting at element 4*j4, from either storage.
+__device__ __forceinline__ float4 load_row4(const float* __restrict__ x32,
+                                            const __nv_bfloat16* __restrict__ x16, long long row,
+                                            int d, int d_pad, int j4) {
+    if (x32) return __ldg(reinterpret_cast<const float4*>(x32 + row * d) + j4);
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(x16 + row * d_pad) + j4);
+    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -279,7 +332,9 @@ struct FinalizeParams {
     const int* cnt;                   // [slots] entries per slot
     const int* flags;                 // [slots] or nullptr
     const float* q32;                 // [*, d] fp32 queries (rescore)
-    const float* x32;                 // [n, d] fp32 corpus (rescore)
+    const float* x32;                 // [n, d] fp32 corpus (rescore), or nullptr:
+    const __nv_bfloat16* x16;         // [n, d_pad] bf16 corpus when the index stores bf16
+    int d_pad;
     long long row_offset;
     float* out_scores;                // [*, k]
     long long* out_rows;              // [*, k]
@@ -325,10 +380,9 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
         const float4* q4 = reinterpret_cast<const float4*>(sq);
         for (int i = warp; i < n; i += nw) {
             const uint32_t row = key_row(keys[i]);
-            const float4* xr = reinterpret_cast<const float4*>(p.x32 + static_cast<long long>(row) * p.d);
             double acc = 0.0;
             for (int j = lane; j < p.d / 4; j += 32) {
-                const float4 a = __ldg(xr + j);
+                const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j);
                 const float4 b = q4[j];
                 acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
                 acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
@@ -375,8 +429,8 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
 // exact path: fp32 FMA scores for up to EXACT_QB queries, then a multi-CTA radix select
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-exact_scores_kernel(const float* __restrict__ x32, long long n, int d,
-                    const float* __restrict__ q32, const int* __restrict__ qlist, int nqg,
+exact_scores_kernel(const float* __restrict__ x32, const __nv_bfloat16* __restrict__ x16,
+                    long long n, int d, int d_pad, const float* __restrict__ q32, const int* __restrict__ qlist, int nqg,
                     float* __restrict__ scores /*[EXACT_QB, n]*/) {
     extern __shared__ __align__(16) float esq[];   // [EXACT_QB, d]
     for (int i = threadIdx.x; i < EXACT_QB * d; i += blockDim.x) {
@@ -390,12 +444,11 @@ exact_scores_kernel(const float* __restrict__ x32, long long n, int d,
     const int d4 = d / 4;
     const float4* sq4 = reinterpret_cast<const float4*>(esq);
     for (long long r = warp; r < n; r += nwarps) {
-        const float4* xr = reinterpret_cast<const float4*>(x32 + r * d);
         float acc[EXACT_QB];
 #pragma unroll
         for (int b = 0; b < EXACT_QB; b++) acc[b] = 0.f;
         for (int j = lane; j < d4; j += 32) {
-            const float4 xv = __ldg(xr + j);
+            const float4 xv = load_row4(x32, x16, r, d, d_pad, j);
 #pragma unroll
             for (int b = 0; b < EXACT_QB; b++) {
                 const float4 qv = sq4[b * d4 + j];

@@ -37,7 +37,14 @@ enum {
     B2IP_ERR_INTERNAL = -5
 };
 
-enum { B2IP_F32 = 0, B2IP_F16 = 1 };           /* element type of rows handed to b2ip_add */
+enum { B2IP_F32 = 0, B2IP_F16 = 1, B2IP_BF16 = 2 };   /* element type of rows handed to b2ip_add */
+/* how the index keeps its rows in HBM */
+enum {
+    B2IP_STORE_F32 = 0,  /* fp32 master rows (+ a bf16 shadow for the coarse pass): faiss semantics  */
+    B2IP_STORE_BF16 = 2  /* rows ARE bf16 (rounded to nearest at ingest unless given as bf16); the
+                            search is exact w.r.t. those stored values, rescored in fp32 (BASELINE
+                            config 4).  Half the memory, no shadow copy.                        */
+};
 enum { B2IP_MEM_HOST = 0, B2IP_MEM_DEVICE = 1 };
 
 /* search strategy */
@@ -69,6 +76,9 @@ typedef struct b2ip_stats_s {
 /* replaces faiss.IndexFlatIP(vector_sz)                       -- src/index.py:21
  * d: vector dimension (multiple of 4, <= 4096); device: CUDA ordinal. */
 int b2ip_create(int d, int device, b2ip_handle* out);
+
+/* Same with an explicit storage type (B2IP_STORE_*); b2ip_create == B2IP_STORE_F32. */
+int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out);
 
 /* drops the index and all device memory (the reference relies on GC). */
 void b2ip_destroy(b2ip_handle h);

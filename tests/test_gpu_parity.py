@@ -159,6 +159,53 @@ def test_unnormalised_and_fp16_inputs(fo):
     np.testing.assert_array_equal(e.export_rows(10, 5), x[10:15].astype(np.float32))
 
 
+def _bf16_round(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).bfloat16().float().numpy()
+
+
+@pytest.mark.parametrize("mode", ["tensor", "exact"])
+@pytest.mark.parametrize("k", [10, 100, 1000])
+def test_bf16_storage_is_exact_on_the_stored_values(fo, mode, k):
+    """BASELINE config 4: corpus stored in bf16, fp32 rescore.  The oracle sees the
+    bf16-rounded rows widened to fp32 -- 'the same inputs'."""
+    import torch
+    from b2ip import Engine
+    x = synth(30000, 768, 51)
+    q = synth(48, 768, 52)
+    xr = _bf16_round(x)
+    e = Engine(768, 0, store="bf16")
+    e.add(x[:10000])                                             # fp32 host rows, rounded at ingest
+    e.add(torch.from_numpy(x[10000:20000]).cuda())               # fp32 device rows
+    e.add(torch.from_numpy(x[20000:]).cuda().bfloat16())         # bf16 device rows
+    np.testing.assert_array_equal(e.export_rows(9990, 20), xr[9990:10010])
+    np.testing.assert_array_equal(e.export_rows(19990, 20), xr[19990:20010])
+    D, I = e.search(q, k, mode=mode)
+    Do, Io = fo.search(q, xr, k)
+    fo.compare_topk(D, I, Do, Io, q, xr, rtol=RTOL)
+    assert e.stats()["fallback_queries"] == 0
+
+
+def test_bf16_storage_fp16_host_rows_and_rejects_bf16_on_f32_index(fo):
+    import torch
+    from b2ip import B2ipError, Engine
+    x = (synth(5000, 256, 61, normalize=False) * 0.3).astype(np.float16)
+    e = Engine(256, 0, store="bf16")
+    e.add(x)
+    xr = _bf16_round(x.astype(np.float32))
+    q = synth(20, 256, 62)
+    D, I = e.search(q, 50)
+    Do, Io = fo.search(q, xr, 50)
+    fo.compare_topk(D, I, Do, Io, q, xr, rtol=RTOL)
+    f32 = Engine(256, 0)
+    with pytest.raises((B2ipError, KeyError)):
+        f32._lib.b2ip_add  # noqa: B018
+        import ctypes
+        t = torch.zeros((4, 256), dtype=torch.bfloat16, device="cuda")
+        from b2ip._lib import B2IP_BF16, MEM_DEVICE, check
+        check(f32._lib.b2ip_add(f32._h, 4, ctypes.c_void_p(t.data_ptr()), B2IP_BF16, MEM_DEVICE), f32._h)
+
+
 def test_incremental_adds_equal_one_add(fo):
     x = synth(7000, 768, 21)
     q = synth(20, 768, 22)

@@ -14,7 +14,8 @@ ap.add_argument("--n-queries", type=int, default=100_000)
 ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--d", type=int, default=768)
 ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--sweep", default="gx=32")
+ap.add_argument("--sweep", default="gx=16")
+ap.add_argument("--verbose", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 e = Engine(a.d, 0)
@@ -29,6 +30,7 @@ g = torch.Generator(device=dev).manual_seed(4321)
 q = torch.randn((a.n_queries, a.d), generator=g, device=dev)
 q /= q.norm(dim=1, keepdim=True)
 e.use_torch_stream()
+e.set_option("verbose", a.verbose)
 for cfg in a.sweep.split(";"):
     opts = dict(kv.split("=") for kv in cfg.split(",") if kv)
     for name, v in opts.items():
