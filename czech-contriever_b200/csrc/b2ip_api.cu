@@ -65,6 +65,7 @@ struct b2ip_index_s {
     int hint_q = 0, hint_x = 0;           // 0 normal, 1 evict_first, 2 evict_last
     int dbg = 0;
     int verbose = 0;
+    int pair = 1;                         // use the CTA-pair (cta_group::2) scoring kernel when nq > 128
     long long cand_budget_bytes = 6ll << 30;
 };
 
@@ -272,6 +273,10 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
 
     CU_TRY(h, cudaFuncSetAttribute(coarse_filter_kernel<false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES));
+    CU_TRY(h, cudaFuncSetAttribute(coarse_filter_pair_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+    CUtensorMap tmap_x_pair;
+    RC_TRY(make_tmap_bf16(h, &tmap_x_pair, h->x16, n, h->d_pad, 128));
     const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
     CU_TRY(h, cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(fin_smem)));
@@ -294,10 +299,11 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         h->stats.total_launches++;
         CUtensorMap tmap_q;
         RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, nqb, h->d_pad, TILE_Q));
+        const bool use_pair = h->pair && nqb > TILE_Q && h->sm_count >= 2;
 
         CoarseParams cp{};
         cp.num_k_blocks = h->d_pad / KBLOCK_ELEMS;
-        cp.q_tiles = (nqb + TILE_Q - 1) / TILE_Q;
+        cp.q_tiles = use_pair ? (nqb + 2 * TILE_Q - 1) / (2 * TILE_Q) : (nqb + TILE_Q - 1) / TILE_Q;
         cp.gx = h->gx;
         cp.nq = nqb;
         cp.thr = reinterpret_cast<float*>(h->thr.p);
@@ -322,11 +328,17 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             cp.x_row_end = done + s;
             cp.x_tiles = static_cast<int>((s + TILE_X - 1) / TILE_X);
             const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
-            const int grid = static_cast<int>(std::min<long long>(tiles, h->sm_count));
             cudaEvent_t e0 = get_event(h, ev_used++), e1 = get_event(h, ev_used++);
             CU_TRY(h, cudaEventRecord(e0, h->stream));
-            coarse_filter_kernel<false><<<grid, COARSE_THREADS, COARSE_SMEM_BYTES, h->stream>>>(
-                tmap_q, tmap_x, cp);
+            if (use_pair) {
+                const int grid = 2 * static_cast<int>(std::min<long long>(tiles, h->sm_count / 2));
+                coarse_filter_pair_kernel<<<grid, COARSE_THREADS, PAIR_SMEM_BYTES, h->stream>>>(
+                    tmap_q, tmap_x_pair, cp);
+            } else {
+                const int grid = static_cast<int>(std::min<long long>(tiles, h->sm_count));
+                coarse_filter_kernel<false><<<grid, COARSE_THREADS, COARSE_SMEM_BYTES, h->stream>>>(
+                    tmap_q, tmap_x, cp);
+            }
             CU_TRY(h, cudaEventRecord(e1, h->stream));
             refresh_threshold_kernel<<<nqb, SEL_THREADS, 0, h->stream>>>(
                 k, cap, cp.cand, cp.cnt, reinterpret_cast<int*>(h->kept.p),
@@ -533,6 +545,7 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "hint_x") h->hint_x = static_cast<int>(value);
     else if (n == "dbg") h->dbg = static_cast<int>(value);
     else if (n == "verbose") h->verbose = static_cast<int>(value);
+    else if (n == "pair") h->pair = static_cast<int>(value);
     else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;
     else return fail(h, B2IP_ERR_INVALID, "b2ip_set_option: unknown option '%s'", name);
     return B2IP_OK;

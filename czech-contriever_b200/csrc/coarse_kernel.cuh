@@ -91,6 +91,53 @@ __device__ __forceinline__ void flush_hits(const CoarseParams& p, int q,
         if (slot + i < p.cap) dst[slot + i] = my_stage[i * 128];
 }
 
+// The fused filter: one thread = one query row (TMEM lane) of a 128 x 256 fp32 accumulator.
+// 32 columns at a time: tcgen05.ld, FMNMX3 tree -> chunk maximum, one compare against the
+// row's threshold.  Only if it passes (rare): branch-free hit mask, hits staged in shared
+// memory (flushed once per tile, after the accumulator is released) -- or, for dense chunks
+// (early slabs), appended straight from registers with one counter bump per chunk.
+__device__ __forceinline__ void filter_accumulator(const CoarseParams& p, int q, float thr,
+                                                   uint32_t taddr, long long x_row, int n_valid,
+                                                   unsigned long long* my_stage, int& n_staged) {
+#pragma unroll 1
+    for (int c = 0; c < TILE_X / 32; c++) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+        float m = __uint_as_float(v[0]);
+#pragma unroll
+        for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(v[j]));
+        if (m > thr) {
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+            const int vcols = n_valid - c * 32;          // columns of this chunk in range
+            if (vcols < 32) mask &= vcols > 0 ? ((1u << vcols) - 1u) : 0u;
+            const uint32_t row0 = static_cast<uint32_t>(x_row) + c * 32;
+            const int nh = __popc(mask);
+            if (n_staged + nh > HIT_SLOTS) {
+                int slot = atomicAdd(p.cnt + q, nh);
+                unsigned long long* dst = p.cand + static_cast<long long>(q) * p.cap;
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t bits = select32(v, j);
+                    if (slot < p.cap) dst[slot] = make_key(__uint_as_float(bits), row0 + j);
+                    slot++;
+                }
+            } else {
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t bits = select32(v, j);
+                    my_stage[n_staged * 128] = make_key(__uint_as_float(bits), row0 + j);
+                    n_staged++;
+                }
+            }
+        }
+    }
+}
+
 template <bool kDump>
 __global__ void __launch_bounds__(COARSE_THREADS, 1)
 coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -213,12 +260,12 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
             ptx::tc_fence_after();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * TILE_X);
+            if (kDump) {
 #pragma unroll 1
-            for (int c = 0; c < ((p.dbg & 4) ? 0 : TILE_X / 32); c++) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(taddr + c * 32, v);
-                ptx::tmem_ld_wait();
-                if (kDump) {
+                for (int c = 0; c < TILE_X / 32; c++) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + c * 32, v);
+                    ptx::tmem_ld_wait();
                     if (q < p.nq) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
@@ -228,46 +275,9 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                        static_cast<long long>(xt) * TILE_X + col] = __uint_as_float(v[j]);
                         }
                     }
-                } else {
-                    float m = __uint_as_float(v[0]);
-#pragma unroll
-                    for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(v[j]));
-                    if (m > thr) {
-                        // rare path: at least one of this thread's 32 scores is a candidate.
-                        // Branch-free hit mask, ONE counter bump for all hits of the chunk,
-                        // then only the hit columns are pulled out with a select tree.
-                        uint32_t mask = 0;
-#pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
-                        const int vcols = n_valid - c * 32;          // columns of this chunk in range
-                        if (vcols < 32) mask &= vcols > 0 ? ((1u << vcols) - 1u) : 0u;
-                        const uint32_t row0 = static_cast<uint32_t>(x_row) + c * 32;
-                        const int nh = __popc(mask);
-                        if (n_staged + nh > HIT_SLOTS) {
-                            // dense chunk (early slabs): append straight from registers
-                            int slot = atomicAdd(p.cnt + q, nh);
-                            unsigned long long* dst = p.cand + static_cast<long long>(q) * p.cap;
-                            while (mask) {
-                                const int j = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                const uint32_t bits = select32(v, j);
-                                if (slot < p.cap) dst[slot] = make_key(__uint_as_float(bits), row0 + j);
-                                slot++;
-                            }
-                        } else {
-                            // sparse chunk (the bulk of the work): stage in shared memory, the
-                            // global append happens once per tile after the accumulator is released
-                            while (mask) {
-                                const int j = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                const uint32_t bits = select32(v, j);
-                                my_stage[n_staged * 128] = make_key(__uint_as_float(bits), row0 + j);
-                                n_staged++;
-                            }
-                        }
-                    }
                 }
+            } else if (!(p.dbg & 4)) {
+                filter_accumulator(p, q, thr, taddr, x_row, n_valid, my_stage, n_staged);
             }
             // hand the accumulator back before touching global memory: the (latency-bound)
             // counter bump + key stores then overlap the MMAs of the following tiles
@@ -283,6 +293,164 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// =======================================================================================
+// CTA-pair variant (cta_group::2): one 256-query x 256-row tile per cluster of two SMs.
+// Each CTA stages ITS 128 query rows (A half) and ITS 128 corpus rows (B half) -- 32 KiB per
+// k-block instead of 48 KiB, a third less L2->SM and smem->tensor-core operand traffic per
+// flop -- the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), each CTA filters the 128
+// accumulator rows that land in its own TMEM.
+//   full[s]   : leader's barrier; leader arrives with expect_tx(64 KiB), both CTAs' TMA loads
+//               complete_tx on it
+//   empty[s]  : per CTA; tcgen05.commit multicast to both when the stage's MMAs retire
+//   tfull[a]  : per CTA; commit multicast when an accumulator is complete
+//   tempty[a] : leader's barrier; 256 arrivals = epilogue threads of both CTAs
+// =======================================================================================
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_HALF_BYTES = 128 * KBLOCK_BYTES;            // 16 KiB: 128 rows x 128 B
+constexpr int PAIR_STAGE_BYTES = 2 * PAIR_HALF_BYTES;          // A half + B half per CTA
+constexpr int PAIR_SMEM_BYTES =
+    PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256 + HIT_STAGE_BYTES;
+constexpr uint32_t IDESC_BF16_PAIR = ptx::umma_idesc(/*bf16*/ 1, 256, TILE_X);
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(COARSE_THREADS, 1)
+coarse_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                          const __grid_constant__ CUtensorMap tmap_x, const CoarseParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + PAIR_STAGES * PAIR_HALF_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PAIR_STAGES * PAIR_STAGE_BYTES);
+    uint64_t* full_bar = bars;                            // [PAIR_STAGES]
+    uint64_t* empty_bar = bars + PAIR_STAGES;             // [PAIR_STAGES]
+    uint64_t* tfull_bar = bars + 2 * PAIR_STAGES;         // [2]
+    uint64_t* tempty_bar = bars + 2 * PAIR_STAGES + 2;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PAIR_STAGES + 4);
+    unsigned long long* hit_stage =
+        reinterpret_cast<unsigned long long*>(smem + PAIR_STAGES * PAIR_STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();         // 0 = leader
+    const int cluster_id = blockIdx.x >> 1;
+    const int n_clusters = gridDim.x >> 1;
+    // p.q_tiles counts 256-query pair tiles here
+    const int total_tiles = p.q_tiles * p.x_tiles;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_q);
+        ptx::prefetch_tmap(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < PAIR_STAGES; s++) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 256);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();              // peer barriers initialised before any remote signal
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer (both CTAs) =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+                int qt, xt;
+                tile_coords(p, t, qt, xt);
+                const int q_row = qt * 256 + static_cast<int>(rank) * 128;
+                const long long x_row =
+                    p.x_row0 + static_cast<long long>(xt) * TILE_X + static_cast<long long>(rank) * 128;
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
+                    ptx::tma_load_2d_pair(smem_a + stage * PAIR_HALF_BYTES, &tmap_q, &full_bar[stage],
+                                          kb * KBLOCK_ELEMS, q_row, p.hint_q);
+                    ptx::tma_load_2d_pair(smem_b + stage * PAIR_HALF_BYTES, &tmap_x, &full_bar[stage],
+                                          kb * KBLOCK_ELEMS, static_cast<int32_t>(x_row), p.hint_x);
+                    if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * TILE_X);
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem_a + stage * PAIR_HALF_BYTES);
+                    const uint32_t b_addr = ptx::smem_u32(smem_b + stage * PAIR_HALF_BYTES);
+#pragma unroll
+                    for (int k = 0; k < KBLOCK_BYTES / UMMA_K_BYTES; k++) {
+                        const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr + k * UMMA_K_BYTES);
+                        const uint64_t bdesc = ptx::umma_desc_k_sw128(b_addr + k * UMMA_K_BYTES);
+                        ptx::mma_f16_ss_pair(d_tmem, adesc, bdesc, IDESC_BF16_PAIR, (kb | k) != 0);
+                    }
+                    ptx::tc_commit_pair(&empty_bar[stage], 0x3);
+                    if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::tc_commit_pair(&tfull_bar[as], 0x3);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== filter epilogue (both CTAs, own 128 rows) =====================
+        const int wq = warp & 3;
+        int as = 0;
+        uint32_t aphase = 0;
+        const uint32_t tempty_leader0 = ptx::mapa_u32(&tempty_bar[0], 0);
+        const uint32_t tempty_leader1 = ptx::mapa_u32(&tempty_bar[1], 0);
+        for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+            int qt, xt;
+            tile_coords(p, t, qt, xt);
+            const int q = qt * 256 + static_cast<int>(rank) * 128 + wq * 32 + lane;
+            unsigned long long* my_stage = hit_stage + (wq * 32 + lane);
+            int n_staged = 0;
+            const long long x_row = p.x_row0 + static_cast<long long>(xt) * TILE_X;
+            const long long left = p.x_row_end - x_row;
+            const int n_valid = left < TILE_X ? static_cast<int>(left) : TILE_X;
+            float thr = __int_as_float(0x7f800000);
+            if (q < p.nq) thr = __ldg(p.thr + q);
+
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * TILE_X);
+            if (!(p.dbg & 4)) filter_accumulator(p, q, thr, taddr, x_row, n_valid, my_stage, n_staged);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive_cluster(as == 0 ? tempty_leader0 : tempty_leader1);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+            if (n_staged) flush_hits(p, q, my_stage, n_staged);
+        }
+    }
+
+    // nobody may leave (or free TMEM) while the peer can still signal / be read
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_pair<TMEM_COLS>(tmem_base);
     }
 }
 
