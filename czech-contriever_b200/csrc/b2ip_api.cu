@@ -65,7 +65,7 @@ struct b2ip_index_s {
     int hint_q = 0, hint_x = 0;           // 0 normal, 1 evict_first, 2 evict_last
     int dbg = 0;
     int verbose = 0;
-    int pair = 1;                         // use the CTA-pair (cta_group::2) scoring kernel when nq > 128
+    int pair = 0;                         // 1: CTA-pair (cta_group::2) scoring kernel when nq > 128 (measured 5-10 % slower)
     long long cand_budget_bytes = 6ll << 30;
 };
 
