@@ -333,9 +333,18 @@ def main():
     achieved = flops_rank / (agg["coarse_ms"] / 1e3) / 1e12 if agg["coarse_ms"] > 0 else 0.0
     achieved = -max_over_ranks(-achieved)     # slowest rank
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    traffic, traffic_note = None, None
+    try:   # dram bytes of the scoring kernel from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r1_coarse_ncu.json")) as f:
+            prof = json.load(f)
+        traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+        traffic_note = (f"ncu capture of one launch ({prof['launch']}, {prof['flops']:.3e} FLOP, "
+                        f"{prof['duration_ms']:.1f} ms): dram read+write bytes; {prof['source']}")
+    except Exception:
+        pass
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
         "kernel": "coarse_filter_kernel<false> (tcgen05.mma kind::f16, fused threshold filter)",
         "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a multi-second step)",
         "burst_peak": peaks.get("bf16_tflops"),
