@@ -61,11 +61,11 @@ struct b2ip_index_s {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     b2ip_stats_t stats;
     std::string err;
-    int gx = 16;
+    int gx = 0;                           // x-tiles per raster group; 0 = sm_count / 2
     int hint_q = 0, hint_x = 0;           // 0 normal, 1 evict_first, 2 evict_last
     int dbg = 0;
     int verbose = 0;
-    int pair = 0;                         // 1: CTA-pair (cta_group::2) scoring kernel when nq > 128 (measured 5-10 % slower)
+    int pair = 1;                         // CTA-pair (cta_group::2) scoring kernel when nq > 128
     long long cand_budget_bytes = 6ll << 30;
 };
 
@@ -505,6 +505,8 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
         qres != cudaDriverEntryPointSuccess || !fn)
         return bail(B2IP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    h->gx = std::max(1, h->sm_count / 2);   // = clusters of the pair kernel: one query tile per wave,
+                                            // the corpus tiles of a group stay L2 resident (measured best)
     if (const char* s = getenv("B2IP_GX")) h->gx = std::max(1, atoi(s));
     if (const char* s = getenv("B2IP_CAND_BUDGET_MB")) h->cand_budget_bytes = std::max(1ll, atoll(s)) << 20;
     memset(&h->stats, 0, sizeof(h->stats));
