@@ -61,6 +61,10 @@ class ShardedIndex:
             self.segments.append((self._n_local, int(global_start), n))
         self._n_local += n
         self._seg_cache = None
+        # one contiguous segment: the engine adds the offset itself (no extra kernels per search)
+        if hasattr(self.engine, "set_row_offset"):
+            self.engine.set_row_offset(self.segments[0][1] - self.segments[0][0]
+                                       if len(self.segments) == 1 else 0)
 
     def add_replicated(self, rows) -> None:
         """SPMD ingest: every rank is handed the SAME chunk (the reference's `index_data`
@@ -81,6 +85,8 @@ class ShardedIndex:
         if not self.segments:
             return rows_local
         if len(self.segments) == 1:
+            if hasattr(self.engine, "set_row_offset"):
+                return rows_local                      # offset already applied by the engine
             ls, gs, _ = self.segments[0]
             return torch.where(rows_local >= 0, rows_local + (gs - ls), rows_local)
         if self._seg_cache is None or self._seg_cache[0].device != rows_local.device:

@@ -320,6 +320,17 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         int64_t slab = std::min<int64_t>(cap, std::max<int64_t>(1024, 8ll * k));
         slab = slab / TILE_X * TILE_X;
         long long overflowed = 0;
+        // Latency regime (small query batches): a FIXED geometric slab schedule, no host
+        // round-trip between slabs.  Growth r is chosen so that ~3k*r expected new hits stay below
+        // half the list capacity; a list that overflows anyway sends its query to the exact path.
+        const bool fixed_schedule = nqb <= 2048 && n > slab;
+        double growth = 0.0;
+        if (fixed_schedule) {
+            const double r_max = std::max(2.0, 0.5 * cap / (3.0 * k));
+            const double span = static_cast<double>(n) / static_cast<double>(slab);
+            const int steps = std::max(1, static_cast<int>(std::ceil(std::log(span) / std::log(r_max))));
+            growth = std::pow(span, 1.0 / steps);
+        }
         while (done < n) {
             int64_t s = std::min<int64_t>(slab, n - done);
             if (done + s < n) s = std::max<int64_t>(TILE_X, s / TILE_X * TILE_X);
@@ -344,15 +355,20 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
                 k, cap, cp.cand, cp.cnt, reinterpret_cast<int*>(h->kept.p),
                 reinterpret_cast<float*>(h->thr.p), reinterpret_cast<float*>(h->eps2.p),
                 reinterpret_cast<int*>(h->flags.p), h->gstats);
-            CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
-                                      cudaMemcpyDeviceToHost, h->stream));
-            CU_TRY(h, cudaStreamSynchronize(h->stream));
-            CU_TRY(h, cudaGetLastError());
             h->stats.coarse_launches++;
             h->stats.total_launches += 2;
             h->stats.slabs++;
             h->stats.coarse_flops += 2.0 * nqb * static_cast<double>(s) * h->d;
             done += s;
+            if (fixed_schedule) {
+                slab = std::max<int64_t>(TILE_X, static_cast<int64_t>(static_cast<double>(done) * (growth - 1.0)));
+                if (n - done - slab < slab / 4) slab = n - done;          // no tiny tail slab
+                continue;
+            }
+            CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
+                                      cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            CU_TRY(h, cudaGetLastError());
             const long long m_max = std::max<long long>(h->h_gstats[GS_MAX_KEPT], 1);
             overflowed = h->h_gstats[GS_OVERFLOW];
             if (h->verbose) {
@@ -370,7 +386,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             next = std::min(next, 4.0e9);
             slab = std::max<int64_t>(TILE_X, static_cast<int64_t>(next));
         }
-        h->stats.candidates += h->h_gstats[GS_CANDIDATES];
+        if (!fixed_schedule) h->stats.candidates += h->h_gstats[GS_CANDIDATES];
 
         FinalizeParams fp{};
         fp.k = k; fp.cap = cap; fp.d = h->d;
@@ -389,7 +405,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
                                   cudaMemcpyDeviceToHost, h->stream));
         std::vector<int> hflags;
-        if (overflowed > 0) {
+        if (overflowed > 0 || fixed_schedule) {
             hflags.resize(nqb);
             CU_TRY(h, cudaMemcpyAsync(hflags.data(), h->flags.p, nqb * sizeof(int),
                                       cudaMemcpyDeviceToHost, h->stream));
@@ -397,6 +413,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         CU_TRY(h, cudaGetLastError());
         h->stats.rescored += h->h_gstats[GS_RESCORED];
+        if (fixed_schedule) h->stats.candidates += h->h_gstats[GS_CANDIDATES];
         for (int i = 0; i < static_cast<int>(hflags.size()); i++)
             if (hflags[i] & FLAG_OVERFLOW) fallback.push_back(static_cast<int>(q0 + i));
     }

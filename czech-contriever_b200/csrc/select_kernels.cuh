@@ -16,6 +16,7 @@ namespace b2ip {
 
 constexpr int SEL_THREADS = 256;
 constexpr int SORT_CAP = 4096;       // u64 keys sorted in shared memory by finalize
+constexpr int REFRESH_SMEM_KEYS = 4096;   // candidate lists up to this size are refreshed from smem
 constexpr int FLAG_OVERFLOW = 1;
 constexpr int EXACT_QB = 8;          // queries per pass of the exact path
 
@@ -241,7 +242,7 @@ __device__ unsigned long long block_radix_select(const unsigned long long* __res
 
 // In-place stream compaction of keys[0..n): keeps keys whose high word is > hi_thr
 // (or, with by_key, keys >= key_thr).  Returns the number kept (all threads).
-__device__ int block_compact(unsigned long long* keys, int n, bool by_key, uint32_t hi_thr,
+__device__ int block_compact(const unsigned long long* keys, int n, bool by_key, uint32_t hi_thr,
                              unsigned long long key_thr, unsigned long long* out, int* s_warp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int base_out = 0;
@@ -308,11 +309,20 @@ refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
         return;
     }
     unsigned long long* keys = cand + static_cast<long long>(q) * cap;
-    const unsigned long long pk = block_radix_select(keys, n, k, 4, hist, &s_prefix, &s_krem);
+    // lists that fit are pulled into shared memory once: the 4 select passes and the
+    // compaction then never touch L2 again
+    __shared__ unsigned long long skeys[REFRESH_SMEM_KEYS];
+    const unsigned long long* src = keys;
+    if (n <= REFRESH_SMEM_KEYS) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[i] = keys[i];
+        __syncthreads();
+        src = skeys;
+    }
+    const unsigned long long pk = block_radix_select(src, n, k, 4, hist, &s_prefix, &s_krem);
     const float ck = unorder_f32(static_cast<uint32_t>(pk >> 32));
     float t = __fsub_rd(ck, eps2[q]);
     t = nextafterf(t, -INFINITY);                    // admission test is strict
-    const int m = block_compact(keys, n, false, order_f32(t), 0ull, keys, s_warp);
+    const int m = block_compact(src, n, false, order_f32(t), 0ull, keys, s_warp);
     if (threadIdx.x == 0) {
         cnt[q] = m;
         kept[q] = m;

@@ -78,6 +78,37 @@ def test_search_matches_oracle(fo, mode, n, nq, k, d):
         assert st["coarse_launches"] >= 1 and st["fallback_queries"] == 0
 
 
+@pytest.mark.parametrize("nq", [1, 2, 16, 64, 128, 129, 2048])
+@pytest.mark.parametrize("k", [10, 100])
+def test_small_query_batches_latency_regime(fo, nq, k):
+    """BASELINE config 5 regime: batches of 1-64 queries (fixed, sync-free slab schedule up to
+    2048 queries) over a corpus that spans several slabs."""
+    x = synth(200_000, 768, 1234)
+    q = synth(nq, 768, 4321)
+    e = _engine(x)
+    D, I = e.search(q, k)
+    st = e.stats()
+    assert st["slabs"] >= 2 and st["fallback_queries"] == 0
+    Do, Io = fo.search(q, x, k)
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+
+
+@pytest.mark.parametrize("nq", [8, 3000])
+def test_ascending_scores_overflow_every_list(fo, nq):
+    """Adversarial order: rows sorted by increasing score, every row beats the running threshold,
+    the candidate lists overflow (in both slab schedules) and the exact path takes over."""
+    u = synth(1, 128, 3)[0]
+    n = 60_000
+    x = (u[None, :] * (1.0 + np.arange(n, dtype=np.float32)[:, None] * 1e-5)).astype(np.float32)
+    q = np.tile(u[None, :], (nq, 1)) * np.linspace(0.5, 1.5, nq, dtype=np.float32)[:, None]
+    e = _engine(x)
+    D, I = e.search(q, 100)
+    assert e.stats()["fallback_queries"] > 0
+    Do, Io = fo.search(q, x, 100)
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+    assert np.array_equal(I[0], np.arange(n - 1, n - 101, -1))
+
+
 def test_c1_full_config(fo):
     """BASELINE config 1 in full: 100k x 768 corpus, 1k queries, k=100."""
     x = synth(100_000, 768, 1234)
