@@ -11,12 +11,14 @@ ap.add_argument("--n-corpus", type=int, default=2_625_000)
 ap.add_argument("--d", type=int, default=768)
 ap.add_argument("--cases", default="100000:100,100000:1000,10000:100,1:10,4:10,16:10,64:10,256:10,2048:100")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--store", default="f32")
+ap.add_argument("--verbose", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 
 
 def build(n):
-    e = Engine(a.d, 0)
+    e = Engine(a.d, 0, store=a.store)
     e.reserve(n)
     CH = 1 << 18
     for c0 in range(0, n, CH):
@@ -25,6 +27,7 @@ def build(n):
         x /= x.norm(dim=1, keepdim=True)
         e.add(x)
     e.use_torch_stream()
+    e.set_option("verbose", a.verbose)
     return e
 
 
