@@ -388,19 +388,33 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
             sq[j] = p.q32[static_cast<long long>(q) * p.d + j];
         __syncthreads();
         const float4* q4 = reinterpret_cast<const float4*>(sq);
-        for (int i = warp; i < n; i += nw) {
+        // two candidates per warp iteration: both rows' loads are in flight before either
+        // reduction starts (the gather is latency-bound: 3 KB from a random HBM page per row)
+        for (int i = warp; i < n; i += 2 * nw) {
+            const int i2 = i + nw;
+            const bool has2 = i2 < n;
             const uint32_t row = key_row(keys[i]);
-            double acc = 0.0;
+            const uint32_t row2 = has2 ? key_row(keys[i2]) : row;
+            double acc = 0.0, acc2 = 0.0;
             for (int j = lane; j < p.d / 4; j += 32) {
                 const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j);
+                const float4 a2 = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j);
                 const float4 b = q4[j];
                 acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
                 acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
                 acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
                 acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
+                acc2 = fma(static_cast<double>(a2.x), static_cast<double>(b.x), acc2);
+                acc2 = fma(static_cast<double>(a2.y), static_cast<double>(b.y), acc2);
+                acc2 = fma(static_cast<double>(a2.z), static_cast<double>(b.z), acc2);
+                acc2 = fma(static_cast<double>(a2.w), static_cast<double>(b.w), acc2);
             }
             acc = warp_sum(acc);
-            if (lane == 0) keys[i] = make_key(static_cast<float>(acc), row);   // NaN -> high word 0
+            acc2 = warp_sum(acc2);
+            if (lane == 0) {
+                keys[i] = make_key(static_cast<float>(acc), row);   // NaN -> high word 0
+                if (has2) keys[i2] = make_key(static_cast<float>(acc2), row2);
+            }
         }
         if (threadIdx.x == 0 && p.gstats)
             atomicAdd(reinterpret_cast<unsigned long long*>(p.gstats + GS_RESCORED),
