@@ -36,6 +36,7 @@ class Stats(ctypes.Structure):
         ("candidates", ctypes.c_int64), ("rescored", ctypes.c_int64),
         ("fallback_queries", ctypes.c_int64),
         ("slabs", ctypes.c_int32), ("query_batches", ctypes.c_int32),
+        ("refresh_ms", ctypes.c_float), ("finalize_ms", ctypes.c_float),
     ]
 
     def as_dict(self) -> dict:

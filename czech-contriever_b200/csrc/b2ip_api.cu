@@ -57,7 +57,7 @@ struct b2ip_index_s {
     // grow-only workspace
     DevBuf q16, eps2, thr, cnt, kept, flags, cand, qstage, out_s, out_r, exact_scores, exact_misc,
         qlist, stage;
-    std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> ev_pool, ev_fin;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     b2ip_stats_t stats;
     std::string err;
@@ -182,14 +182,15 @@ unsigned long long hint_policy(int v) {
     return v == 1 ? ptx::kEvictFirst : (v == 2 ? ptx::kEvictLast : ptx::kEvictNormal);
 }
 
-cudaEvent_t get_event(b2ip_handle h, size_t i) {
-    while (h->ev_pool.size() <= i) {
+cudaEvent_t get_event(std::vector<cudaEvent_t>& pool, size_t i) {
+    while (pool.size() <= i) {
         cudaEvent_t e;
         cudaEventCreate(&e);
-        h->ev_pool.push_back(e);
+        pool.push_back(e);
     }
-    return h->ev_pool[i];
+    return pool[i];
 }
+cudaEvent_t get_event(b2ip_handle h, size_t i) { return get_event(h->ev_pool, i); }
 
 struct Guard {   // selects the index's device for the duration of a call
     int prev = -1;
@@ -355,6 +356,8 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
                 k, cap, cp.cand, cp.cnt, reinterpret_cast<int*>(h->kept.p),
                 reinterpret_cast<float*>(h->thr.p), reinterpret_cast<float*>(h->eps2.p),
                 reinterpret_cast<int*>(h->flags.p), h->gstats);
+            cudaEvent_t e2 = get_event(h, ev_used++);
+            CU_TRY(h, cudaEventRecord(e2, h->stream));
             h->stats.coarse_launches++;
             h->stats.total_launches += 2;
             h->stats.slabs++;
@@ -400,7 +403,11 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         fp.out_scores = d_scores + q0 * k;
         fp.out_rows = reinterpret_cast<long long*>(d_rows) + q0 * k;
         fp.gstats = h->gstats;
+        cudaEvent_t f0 = get_event(h->ev_fin, 2 * (h->stats.query_batches - 1));
+        cudaEvent_t f1 = get_event(h->ev_fin, 2 * (h->stats.query_batches - 1) + 1);
+        CU_TRY(h, cudaEventRecord(f0, h->stream));
         finalize_kernel<true><<<nqb, SEL_THREADS, fin_smem, h->stream>>>(fp);
+        CU_TRY(h, cudaEventRecord(f1, h->stream));
         h->stats.total_launches++;
         CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
                                   cudaMemcpyDeviceToHost, h->stream));
@@ -418,12 +425,38 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             if (hflags[i] & FLAG_OVERFLOW) fallback.push_back(static_cast<int>(q0 + i));
     }
     // scoring-kernel time from the recorded event pairs
-    float ms_sum = 0.f;
-    for (size_t i = 0; i + 1 < ev_used; i += 2) {
+    float ms_sum = 0.f, ref_sum = 0.f, fin_sum = 0.f;
+    for (size_t i = 0; i + 3 <= ev_used; i += 3) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]) == cudaSuccess) ms_sum += ms;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[i + 1], h->ev_pool[i + 2]) == cudaSuccess) ref_sum += ms;
+    }
+    for (int b = 0; b < h->stats.query_batches; b++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_fin[2 * b], h->ev_fin[2 * b + 1]) == cudaSuccess)
+            fin_sum += ms;
     }
     h->stats.coarse_ms = ms_sum;
+    h->stats.refresh_ms = ref_sum;
+    h->stats.finalize_ms = fin_sum;
+    if (h->verbose) {
+        float t = 0.f;
+        for (size_t i = 0; i + 3 <= ev_used; i += 3) {
+            float a = 0.f, b = 0.f, c = 0.f, gap = 0.f;
+            cudaEventElapsedTime(&a, h->ev_t0, h->ev_pool[i]);
+            cudaEventElapsedTime(&b, h->ev_pool[i], h->ev_pool[i + 1]);
+            cudaEventElapsedTime(&c, h->ev_pool[i + 1], h->ev_pool[i + 2]);
+            if (i + 3 < ev_used) cudaEventElapsedTime(&gap, h->ev_pool[i + 2], h->ev_pool[i + 3]);
+            fprintf(stderr, "[b2ip] t=%.3f ms: coarse %.3f refresh %.3f then gap %.3f\n", a, b, c, gap);
+            t = a + b + c;
+        }
+        for (int b = 0; b < h->stats.query_batches; b++) {
+            float a = 0.f, f = 0.f;
+            cudaEventElapsedTime(&a, h->ev_t0, h->ev_fin[2 * b]);
+            cudaEventElapsedTime(&f, h->ev_fin[2 * b], h->ev_fin[2 * b + 1]);
+            fprintf(stderr, "[b2ip] t=%.3f ms: finalize %.3f (last slab ended at %.3f)\n", a, f, t);
+        }
+    }
     if (!fallback.empty()) {
         h->stats.fallback_queries = static_cast<int64_t>(fallback.size());
         RC_TRY(exact_search(h, q32, fallback.data(), static_cast<int64_t>(fallback.size()), k,
@@ -544,6 +577,7 @@ void b2ip_destroy(b2ip_handle h) {
     if (h->gstats) cudaFree(h->gstats);
     if (h->h_gstats) cudaFreeHost(h->h_gstats);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_fin) cudaEventDestroy(e);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -572,7 +606,7 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
 
 int b2ip_reserve(b2ip_handle h, int64_t n_rows) {
     if (!h) return B2IP_ERR_INVALID;
-    if (n_rows < 0 || n_rows >= (1ll << 32)) return fail(h, B2IP_ERR_INVALID, "n_rows=%lld out of range", (long long)n_rows);
+    if (n_rows < 0 || n_rows >= (1ll << 31) - 512) return fail(h, B2IP_ERR_INVALID, "n_rows=%lld out of range", (long long)n_rows);
     Guard g(h->device);
     if (n_rows <= h->cap_rows) return B2IP_OK;
     return grow_rows(h, n_rows, /*exact=*/true);   // a reserve states the final size
@@ -587,7 +621,7 @@ int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem)
     if (src_dtype == B2IP_BF16 && !h->store_bf16)
         return fail(h, B2IP_ERR_INVALID, "b2ip_add: bf16 rows need an index created with B2IP_STORE_BF16");
     if (n == 0) return B2IP_OK;
-    if (h->n + n >= (1ll << 32) - 1) return fail(h, B2IP_ERR_UNSUPPORTED, "a shard holds at most 2^32-2 rows");
+    if (h->n + n >= (1ll << 31) - 512) return fail(h, B2IP_ERR_UNSUPPORTED, "a shard holds at most 2^31-512 rows (TMA coordinates are int32)");
     Guard g(h->device);
     RC_TRY(grow_rows(h, h->n + n));
     const cudaMemcpyKind kind = mem == B2IP_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;

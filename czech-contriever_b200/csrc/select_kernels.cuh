@@ -204,9 +204,24 @@ __device__ unsigned long long block_radix_select(const unsigned long long* __res
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned long long key = keys[i];
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1u);
+        // Scores of one list share their leading bytes, so most lanes of a warp hit the SAME bin:
+        // lanes with equal digits elect one of them to add the whole group's count.
+        for (int base = 0; base < n; base += blockDim.x) {
+            const int i = base + threadIdx.x;
+            unsigned int digit = 256u;                       // 256 = not counted
+            if (i < n) {
+                const unsigned long long key = keys[i];
+                if ((key & mask) == prefix) digit = static_cast<unsigned int>((key >> shift) & 255);
+            }
+            // cheap aggregation for the common case: everyone who agrees with lane 0's digit is
+            // counted by lane 0 in one add, the rest add for themselves
+            const unsigned int first = __shfl_sync(0xffffffffu, digit, 0);
+            const unsigned int same = __ballot_sync(0xffffffffu, digit == first);
+            if ((threadIdx.x & 31) == 0) {
+                if (digit < 256u) atomicAdd(&hist[digit], static_cast<unsigned int>(__popc(same)));
+            } else if (digit < 256u && digit != first) {
+                atomicAdd(&hist[digit], 1u);
+            }
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -270,6 +285,48 @@ __device__ int block_compact(const unsigned long long* keys, int n, bool by_key,
     return base_out;
 }
 
+// Same selection, for `out` NOT aliasing `keys`: each warp owns a contiguous segment, one
+// counting pass, one block barrier, one writing pass (2 barriers instead of 2 per 256 keys).
+__device__ int block_compact_disjoint(const unsigned long long* keys, int n, bool by_key,
+                                      uint32_t hi_thr, unsigned long long key_thr,
+                                      unsigned long long* out, int* s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int seg = ((n + nw - 1) / nw + 31) & ~31;
+    const int b = warp * seg, e = min(n, b + seg);
+    int mine = 0;
+    for (int i0 = b; i0 < e; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false;
+        if (i < e) {
+            const unsigned long long key = keys[i];
+            keep = by_key ? (key >= key_thr) : (static_cast<uint32_t>(key >> 32) > hi_thr);
+        }
+        mine += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (lane == 0) s_warp[warp] = mine;
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < nw; w++) {
+        const int c = s_warp[w];
+        if (w < warp) off += c;
+        tot += c;
+    }
+    for (int i0 = b; i0 < e; i0 += 32) {
+        const int i = i0 + lane;
+        unsigned long long key = 0;
+        bool keep = false;
+        if (i < e) {
+            key = keys[i];
+            keep = by_key ? (key >= key_thr) : (static_cast<uint32_t>(key >> 32) > hi_thr);
+        }
+        const unsigned int ballot = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[off + __popc(ballot & ((1u << lane) - 1u))] = key;
+        off += __popc(ballot);
+    }
+    __syncthreads();
+    return tot;
+}
+
 // ---------------------------------------------------------------------------------------
 // threshold refresh after a slab: one CTA per query
 // ---------------------------------------------------------------------------------------
@@ -322,7 +379,8 @@ refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
     const float ck = unorder_f32(static_cast<uint32_t>(pk >> 32));
     float t = __fsub_rd(ck, eps2[q]);
     t = nextafterf(t, -INFINITY);                    // admission test is strict
-    const int m = block_compact(src, n, false, order_f32(t), 0ull, keys, s_warp);
+    const int m = (src == keys) ? block_compact(src, n, false, order_f32(t), 0ull, keys, s_warp)
+                                : block_compact_disjoint(src, n, false, order_f32(t), 0ull, keys, s_warp);
     if (threadIdx.x == 0) {
         cnt[q] = m;
         kept[q] = m;
@@ -429,7 +487,7 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
     } else {
         // more survivors than the sort buffer: radix-select the k best keys first
         const unsigned long long kth = block_radix_select(keys, n, p.k, 8, hist, &s_prefix, &s_krem);
-        m = block_compact(keys, n, true, 0u, kth, sbuf, s_warp);
+        m = block_compact_disjoint(keys, n, true, 0u, kth, sbuf, s_warp);
     }
     int P = 1;
     while (P < m) P <<= 1;

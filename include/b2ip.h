@@ -71,6 +71,8 @@ typedef struct b2ip_stats_s {
     int64_t fallback_queries;    /* queries re-run on the exact path (buffer overflow)    */
     int32_t slabs;               /* corpus slabs (threshold refresh points)               */
     int32_t query_batches;
+    float refresh_ms;            /* sum of the threshold-refresh kernel durations          */
+    float finalize_ms;           /* rescore + final select/sort kernel durations           */
 } b2ip_stats_t;
 
 /* replaces faiss.IndexFlatIP(vector_sz)                       -- src/index.py:21

@@ -50,7 +50,7 @@ for case in a.cases.split(","):
             best_wall, best = w, e.stats()
     flops = 2.0 * nq * a.n_corpus * a.d
     print(json.dumps({"n": a.n_corpus, "nq": nq, "k": k, "wall_ms": round(best_wall, 3),
-                      "dev_ms": round(best["total_ms"], 3), "coarse_ms": round(best["coarse_ms"], 3),
+                      "dev_ms": round(best["total_ms"], 3), "coarse_ms": round(best["coarse_ms"], 3), "refresh_ms": round(best["refresh_ms"], 3), "finalize_ms": round(best["finalize_ms"], 3),
                       "tflops_wall": round(flops / best_wall / 1e9, 1), "hbm_floor_ms_bf16": round(hbm_ms, 3),
                       "qps": round(nq / best_wall * 1e3, 1), "slabs": best["slabs"], "launches": best["total_launches"],
                       "cand_per_q": round(best["candidates"] / nq, 1), "resc_per_q": round(best["rescored"] / nq, 1),
