@@ -345,7 +345,7 @@ def main():
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-        "kernel": "coarse_filter_kernel<false> (tcgen05.mma kind::f16, fused threshold filter)",
+        "kernel": "coarse_filter_pair_kernel (tcgen05.mma.cta_group::2 kind::f16, fused threshold filter)",
         "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a multi-second step)",
         "burst_peak": peaks.get("bf16_tflops"),
         "flops_per_launch_avg": flops_rank / max(1, agg["coarse_launches"]),
