@@ -5,9 +5,12 @@
 
 One "step" = one pass of the hot path over one batch of synthetic queries: all `n_queries`
 queries against the whole row-sharded corpus (local tcgen05 scoring + fused filter + fp32
-rescore per GPU, then the NCCL all-gather + merge when N > 1).  Workload = BASELINE config 3:
-21M x 768 fp32 L2-normalised synthetic corpus, 100k queries, k = 100 (fits one B200:
+rescore per GPU, then the NCCL all-gather + merge when N > 1).  Default workload = BASELINE
+config 3: 21M x 768 fp32 L2-normalised synthetic corpus, 100k queries, k = 100 (fits one B200:
 64.5 GB fp32 master + 32.3 GB bf16 shadow).  The corpus is fixed as N grows -> "strong".
+`--workload c2|c4|c5` selects the other BASELINE configs for profiles/ (c4: bf16-stored
+corpus, k = 1000; c5: batches of `--n-queries` (default 64) queries, k = 10, HBM roofline);
+the driver's bench line is always the default.
 
 Prints ONE JSON line on rank 0.  `value` = queries/s with queries resident in HBM;
 `e2e` = the same through the reference-facing call with HOST buffers (H2D of the queries and
@@ -32,9 +35,17 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-METRIC = "queries/sec top-100 exact IP search, 21M x 768"
+METRIC = "queries/sec top-100 exact IP search, 21M x 768"   # BASELINE.json metric (default workload)
 UNIT = "queries/s"
 CHUNK = 1 << 18          # rows per generated corpus chunk (seeded by global chunk index)
+
+# BASELINE.json configs.  bound = the roofline that applies to the scoring kernel.
+WORKLOADS = {
+    "c2": {"n_corpus": 1_000_000, "n_queries": 10_000, "k": 100, "store": "f32", "bound": "tensor"},
+    "c3": {"n_corpus": 21_000_000, "n_queries": 100_000, "k": 100, "store": "f32", "bound": "tensor"},
+    "c4": {"n_corpus": 21_000_000, "n_queries": 100_000, "k": 1000, "store": "bf16", "bound": "tensor"},
+    "c5": {"n_corpus": 21_000_000, "n_queries": 64, "k": 10, "store": "f32", "bound": "hbm"},
+}
 
 
 def parse():
@@ -43,15 +54,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2ip", choices=["b2ip", "reference"])
-    ap.add_argument("--n-corpus", type=int, default=21_000_000)
-    ap.add_argument("--n-queries", type=int, default=100_000)
-    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-corpus", type=int, default=None)
+    ap.add_argument("--n-queries", type=int, default=None)
+    ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--d", type=int, default=768)
+    ap.add_argument("--store", default=None, choices=["f32", "bf16", "f16"])
+    ap.add_argument("--shadow", default=None, choices=["bf16", "f16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=1 << 18)
     ap.add_argument("--cpu-sample-queries", type=int, default=4096)
-    return ap.parse_args()
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    for key in ("n_corpus", "n_queries", "k", "store"):
+        if getattr(args, key) is None:
+            setattr(args, key, w[key])
+    args.bound = w["bound"]
+    if args.workload == "c5" and args.steps == 3 and "--steps" not in sys.argv:
+        args.steps = 200      # latency per batch over >= 200 batches after warm-up
+    return args
 
 
 def load_peaks():
@@ -167,7 +189,7 @@ def run_reference(args):
     q /= np.linalg.norm(q, axis=1, keepdims=True)
     info, t = cpu_reference_qps(args, rows, q, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": info["value"], "unit": UNIT,
+        "impl": "reference", "metric": metric_name(args), "value": info["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * args.n_queries / info["value"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -179,14 +201,21 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def metric_name(args):
+    m = args.n_corpus / 1e6
+    return f"queries/sec top-{args.k} exact IP search, {m:g}M x {args.d}"
+
+
 def workload_config(args, world):
+    op = args.store if args.store != "f32" else (args.shadow or "bf16")
+    stored = {"f32": "fp32", "bf16": "bf16-stored", "f16": "fp16-stored"}[args.store]
     return {
-        "workload": (f"C3: {args.n_corpus} x {args.d} fp32 synthetic L2-normalised corpus, "
+        "workload": (f"{args.workload.upper()}: {args.n_corpus} x {args.d} {stored} synthetic L2-normalised corpus, "
                      f"{args.n_queries} queries, k={args.k}"),
         "n_corpus": args.n_corpus, "n_queries": args.n_queries, "k": args.k, "d": args.d,
         "parallelism": f"row-shard x{world} (one process per GPU, NCCL all-gather + merge)",
-        "l2": "inputs exceed L2: every step streams the whole bf16 shadow corpus (2*d bytes/row)",
-        "coarse": "tcgen05 kind::f16 bf16 operands, fp32 accumulate; fp32 rescore (fp64 accumulate)",
+        "l2": f"inputs exceed L2: every step streams the whole {op} operand copy of the corpus (2*d bytes/row)",
+        "coarse": f"tcgen05 kind::f16 {op} operands, fp32 accumulate; fp32 rescore (fp64 accumulate)",
     }
 
 
@@ -238,7 +267,9 @@ def main():
 
     N, nq, k, d = args.n_corpus, args.n_queries, args.k, args.d
     lo, hi = shard_bounds(N, world, rank)
-    index = ShardedIndex(d, device=local_rank)
+    index = ShardedIndex(d, device=local_rank, store=args.store)
+    if args.shadow is not None:
+        index.engine.set_option("shadow_f16", int(args.shadow == "f16"))
     index.engine.reserve(hi - lo)
     t_ing = time.perf_counter()
     sample_host = None
@@ -332,26 +363,47 @@ def main():
     flops_rank = agg["coarse_flops"]
     achieved = flops_rank / (agg["coarse_ms"] / 1e3) / 1e12 if agg["coarse_ms"] > 0 else 0.0
     achieved = -max_over_ranks(-achieved)     # slowest rank
-    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     traffic, traffic_note = None, None
-    try:   # dram bytes of the scoring kernel from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r1_coarse_ncu.json")) as f:
-            prof = json.load(f)
-        traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
-        traffic_note = (f"ncu capture of one launch ({prof['launch']}, {prof['flops']:.3e} FLOP, "
-                        f"{prof['duration_ms']:.1f} ms): dram read+write bytes; {prof['source']}")
-    except Exception:
-        pass
-    roofline = {
-        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-        "kernel": "coarse_filter_pair_kernel (tcgen05.mma.cta_group::2 kind::f16, fused threshold filter)",
-        "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a multi-second step)",
-        "burst_peak": peaks.get("bf16_tflops"),
-        "flops_per_launch_avg": flops_rank / max(1, agg["coarse_launches"]),
-        "launches": agg["coarse_launches"], "kernel_ms_per_step": coarse_ms / args.steps,
-        "kernel_share_of_step": coarse_ms / ms if ms > 0 else None,
-    }
+    if args.bound == "tensor":
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        try:   # dram bytes of the scoring kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r1_coarse_ncu.json")) as f:
+                prof = json.load(f)
+            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+            traffic_note = (f"ncu capture of one launch ({prof['launch']}, {prof['flops']:.3e} FLOP, "
+                            f"{prof['duration_ms']:.1f} ms): dram read+write bytes; {prof['source']}")
+        except Exception:
+            pass
+        roofline = {
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+            "kernel": "coarse_filter_pair_kernel (tcgen05.mma.cta_group::2 kind::f16, fused threshold filter)",
+            "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a multi-second step)",
+            "burst_peak": peaks.get("bf16_tflops"),
+            "flops_per_launch_avg": flops_rank / max(1, agg["coarse_launches"]),
+            "launches": agg["coarse_launches"], "kernel_ms_per_step": coarse_ms / args.steps,
+            "kernel_share_of_step": coarse_ms / ms if ms > 0 else None,
+        }
+    else:
+        # small batches: the same kernel streams the 16-bit operand copy of the shard once per
+        # batch -> HBM-bound.  Algorithmic bytes = rows * d * 2 (what MUST be read); SURVEY 8d's
+        # figure for an fp32-stored corpus (rows * d * 4) is reported next to it.
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bytes_rank = (hi - lo) * d * 2.0 * args.steps
+        gbs = bytes_rank / (agg["coarse_ms"] / 1e3) / 1e9 if agg["coarse_ms"] > 0 else 0.0
+        gbs = -max_over_ranks(-gbs)
+        roofline = {
+            "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+            "traffic": None,
+            "kernel": "coarse_filter_kernel<false> (TMA-streamed 16-bit corpus tiles, tcgen05 scoring, fused filter)",
+            "peak_source": peak_src + " hbm_gbs (copy bandwidth)",
+            "bytes_per_launch_avg": bytes_rank / max(1, agg["coarse_launches"]),
+            "launches": agg["coarse_launches"], "kernel_ms_per_step": coarse_ms / args.steps,
+            "kernel_share_of_step": coarse_ms / ms if ms > 0 else None,
+            "whole_batch_gbs_16bit": (hi - lo) * d * 2.0 / (ms_per_step / 1e3) / 1e9,
+            "whole_batch_gbs_fp32_bytes_survey8d": (hi - lo) * d * 4.0 / (ms_per_step / 1e3) / 1e9,
+            "ms_per_batch": ms_per_step,
+        }
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None
@@ -362,9 +414,10 @@ def main():
     launches = int(sum_over_ranks(agg["launches"]))
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 coarse / f32 rescore",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": f"{args.store if args.store != 'f32' else (args.shadow or 'bf16')} coarse / f32 rescore",
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu,

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libb2ip.so")
 
 B2IP_OK = 0
 B2IP_F32, B2IP_F16, B2IP_BF16 = 0, 1, 2
-STORE_F32, STORE_BF16 = 0, 2
+STORE_F32, STORE_F16, STORE_BF16 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 MODE_AUTO, MODE_TENSOR, MODE_EXACT = 0, 1, 2
 MAX_K = 2048

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (B2IP_BF16, B2IP_F16, B2IP_F32, MEM_DEVICE, MEM_HOST, MODE_AUTO, MODE_EXACT,
-                   MODE_TENSOR, STORE_BF16, STORE_F32, B2ipError, Stats, check)
+                   MODE_TENSOR, STORE_BF16, STORE_F16, STORE_F32, B2ipError, Stats, check)
 
 _MODES = {"auto": MODE_AUTO, "tensor": MODE_TENSOR, "exact": MODE_EXACT}
 
@@ -24,17 +24,24 @@ def _is_torch(x) -> bool:
 
 
 class Engine:
-    def __init__(self, d: int, device: int = 0, store: str = "f32"):
-        """store="f32": fp32 master rows (faiss semantics).  store="bf16": the index keeps rows in
-        bf16 only (rounded at ingest unless handed in as bf16) and is exact w.r.t. those values
-        with an fp32 rescore -- BASELINE config 4, half the HBM."""
+    def __init__(self, d: int, device: int = 0, store: str = "f32", shadow: Optional[str] = None):
+        """store="f32": fp32 master rows (faiss semantics) + a 16-bit shadow for the coarse pass
+        (`shadow` = "bf16" | "f16", default: the library's).  store="bf16" / "f16": the index keeps
+        rows in that 16-bit type only (rounded at ingest unless handed in as such) and is exact
+        w.r.t. those values with an fp32 rescore.  "bf16" is BASELINE config 4 (half the HBM);
+        "f16" is lossless for the reference's default float16 embedding shards
+        (generate_passage_embeddings.py:75-76), which src/index.py:27 merely widens."""
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         self.store = store
-        st = {"f32": STORE_F32, "bf16": STORE_BF16}[store]
+        st = {"f32": STORE_F32, "bf16": STORE_BF16, "f16": STORE_F16}[store]
         check(self._lib.b2ip_create_ex(int(d), int(device), st, ctypes.byref(self._h)), None)
         self.d = int(d)
         self.device = int(device)
+        if shadow is not None:
+            if store != "f32":
+                raise ValueError("shadow= applies to store='f32' only")
+            self.set_option("shadow_f16", {"bf16": 0, "f16": 1}[shadow])
 
     # -- lifetime ------------------------------------------------------------------
     def close(self) -> None:

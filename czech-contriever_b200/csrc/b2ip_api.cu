@@ -27,6 +27,13 @@
 
 using namespace b2ip;
 
+// operand type of the coarse pass when the index keeps fp32 master rows (b2ip_set_option
+// "shadow_f16" / env B2IP_SHADOW override it)
+#ifndef B2IP_DEFAULT_SHADOW
+#define B2IP_DEFAULT_SHADOW SH_BF16
+#endif
+static constexpr int SH_DEFAULT_F32_STORE = B2IP_DEFAULT_SHADOW;
+
 namespace {
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -49,7 +56,8 @@ struct b2ip_index_s {
     float* x32 = nullptr;
     __nv_bfloat16* x16 = nullptr;
     int64_t n = 0, cap_rows = 0, row_offset = 0;
-    bool store_bf16 = false;              // rows ARE bf16: no fp32 master
+    bool store16 = false;                 // rows ARE 16-bit (bf16 or fp16 per `sh`): no fp32 master
+    int sh = SH_BF16;                     // operand type of the coarse GEMM = element type of x16
     unsigned int* norm_stats = nullptr;   // device [2]
     long long* gstats = nullptr;          // device [GS_COUNT]
     long long* h_gstats = nullptr;        // pinned host mirror
@@ -127,7 +135,7 @@ int grow_rows(b2ip_handle h, int64_t need, bool exact = false) {
     __nv_bfloat16* nx16 = nullptr;
     auto alloc_both = [&](int64_t rows) {
         cudaError_t e = cudaSuccess;
-        if (!h->store_bf16) e = cudaMalloc(&nx32, static_cast<size_t>(rows) * h->d * sizeof(float));
+        if (!h->store16) e = cudaMalloc(&nx32, static_cast<size_t>(rows) * h->d * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&nx16, static_cast<size_t>(rows) * h->d_pad * 2);
         return e;
     };
@@ -147,7 +155,7 @@ int grow_rows(b2ip_handle h, int64_t need, bool exact = false) {
                     static_cast<long long>(ncap), cudaGetErrorString(e));
     }
     if (h->n > 0) {
-        if (!h->store_bf16)
+        if (!h->store16)
             CU_TRY(h, cudaMemcpyAsync(nx32, h->x32, static_cast<size_t>(h->n) * h->d * sizeof(float),
                                       cudaMemcpyDeviceToDevice, h->stream));
         CU_TRY(h, cudaMemcpyAsync(nx16, h->x16, static_cast<size_t>(h->n) * h->d_pad * 2,
@@ -168,7 +176,7 @@ int make_tmap_bf16(b2ip_handle h, CUtensorMap* m, const void* base, int64_t rows
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_pad) * 2};
     cuuint32_t box[2] = {KBLOCK_ELEMS, static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+    CUresult r = h->encode(m, h->sh == SH_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -191,6 +199,8 @@ cudaEvent_t get_event(std::vector<cudaEvent_t>& pool, size_t i) {
     return pool[i];
 }
 cudaEvent_t get_event(b2ip_handle h, size_t i) { return get_event(h->ev_pool, i); }
+
+int64_t pad_q(int64_t nq) { return (nq + 2 * TILE_Q - 1) / (2 * TILE_Q) * (2 * TILE_Q); }
 
 struct Guard {   // selects the index's device for the duration of a call
     int prev = -1;
@@ -228,7 +238,7 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
     for (int64_t g0 = 0; g0 < nql; g0 += EXACT_QB) {
         const int nqg = static_cast<int>(std::min<int64_t>(EXACT_QB, nql - g0));
         exact_scores_kernel<<<std::max(sgrid, 1), 256, sq_bytes, h->stream>>>(
-            h->x32, h->x16, n, h->d, h->d_pad, q32, qlist_dev + g0, nqg,
+            h->x32, h->x16, n, h->d, h->d_pad, h->sh, q32, qlist_dev + g0, nqg,
             reinterpret_cast<float*>(h->exact_scores.p));
         exact_init_kernel<<<1, 256, 0, h->stream>>>(st, ghist, gcnt, k);
         for (int pass = 0; pass < 8; pass++) {
@@ -244,7 +254,7 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
         fp.qlist = qlist_dev + g0;
         fp.cand = reinterpret_cast<unsigned long long*>(h->cand.p);
         fp.cnt = gcnt; fp.flags = nullptr; fp.q32 = q32; fp.x32 = h->x32;
-        fp.x16 = h->x16; fp.d_pad = h->d_pad;
+        fp.x16 = h->x16; fp.d_pad = h->d_pad; fp.sh = h->sh;
         fp.row_offset = h->row_offset;
         fp.out_scores = d_scores; fp.out_rows = reinterpret_cast<long long*>(d_rows);
         fp.gstats = nullptr;
@@ -264,7 +274,9 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
     qb_max = std::max<int64_t>(TILE_Q, qb_max / TILE_Q * TILE_Q);
     const int64_t qb = std::min<int64_t>(nq, qb_max);
 
-    RC_TRY(ensure(h, h->q16, static_cast<size_t>(qb) * h->d_pad * 2));
+    // query rows are padded to whole (pair) tiles with zero rows: a TMA box that hangs over
+    // the end of the tensor is served by the (slower) out-of-bounds fill path
+    RC_TRY(ensure(h, h->q16, static_cast<size_t>(pad_q(qb)) * h->d_pad * 2));
     RC_TRY(ensure(h, h->eps2, qb * sizeof(float)));
     RC_TRY(ensure(h, h->thr, qb * sizeof(float)));
     RC_TRY(ensure(h, h->cnt, qb * sizeof(int)));
@@ -296,10 +308,13 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             qptr, reinterpret_cast<__nv_bfloat16*>(h->q16.p), nqb, h->d, h->d_pad, h->norm_stats,
             reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
             reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p),
-            reinterpret_cast<int*>(h->flags.p));
+            reinterpret_cast<int*>(h->flags.p), h->sh);
         h->stats.total_launches++;
+        if (pad_q(nqb) > nqb)
+            CU_TRY(h, cudaMemsetAsync(static_cast<char*>(h->q16.p) + static_cast<size_t>(nqb) * h->d_pad * 2, 0,
+                                      static_cast<size_t>(pad_q(nqb) - nqb) * h->d_pad * 2, h->stream));
         CUtensorMap tmap_q;
-        RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, nqb, h->d_pad, TILE_Q));
+        RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, TILE_Q));
         const bool use_pair = h->pair && nqb > TILE_Q && h->sm_count >= 2;
 
         CoarseParams cp{};
@@ -316,6 +331,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         cp.hint_q = hint_policy(h->hint_q);
         cp.hint_x = hint_policy(h->hint_x);
         cp.dbg = h->dbg;
+        cp.idesc = use_pair ? IDESC_PAIR[h->sh] : IDESC_SINGLE[h->sh];
 
         int64_t done = 0;
         int64_t slab = std::min<int64_t>(cap, std::max<int64_t>(1024, 8ll * k));
@@ -398,7 +414,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         fp.cnt = reinterpret_cast<int*>(h->kept.p);
         fp.flags = reinterpret_cast<int*>(h->flags.p);
         fp.q32 = qptr; fp.x32 = h->x32;
-        fp.x16 = h->x16; fp.d_pad = h->d_pad;
+        fp.x16 = h->x16; fp.d_pad = h->d_pad; fp.sh = h->sh;
         fp.row_offset = h->row_offset;
         fp.out_scores = d_scores + q0 * k;
         fp.out_rows = reinterpret_cast<long long*>(d_rows) + q0 * k;
@@ -409,6 +425,9 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         finalize_kernel<true><<<nqb, SEL_THREADS, fin_smem, h->stream>>>(fp);
         CU_TRY(h, cudaEventRecord(f1, h->stream));
         h->stats.total_launches++;
+        // end of the device-side search (re-recorded after the exact fallback, if any): the
+        // D2H of the counters below and ONE host synchronisation finish the call
+        if (q0 + qb >= nq) CU_TRY(h, cudaEventRecord(h->ev_t1, h->stream));
         CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
                                   cudaMemcpyDeviceToHost, h->stream));
         std::vector<int> hflags;
@@ -461,6 +480,8 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         h->stats.fallback_queries = static_cast<int64_t>(fallback.size());
         RC_TRY(exact_search(h, q32, fallback.data(), static_cast<int64_t>(fallback.size()), k,
                             d_scores, d_rows));
+        CU_TRY(h, cudaEventRecord(h->ev_t1, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
     }
     return B2IP_OK;
 }
@@ -482,10 +503,12 @@ int search_device(b2ip_handle h, int64_t nq, const float* dq, int k, float* d_sc
         RC_TRY(exact_search(h, dq, all.data(), nq, k, d_scores, d_rows));
     } else {
         h->stats.mode_used = B2IP_MODE_TENSOR;
-        RC_TRY(tensor_search(h, dq, nq, k, d_scores, d_rows));
+        RC_TRY(tensor_search(h, dq, nq, k, d_scores, d_rows));   // records ev_t1 and synchronises
     }
-    CU_TRY(h, cudaEventRecord(h->ev_t1, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->stats.mode_used != B2IP_MODE_TENSOR) {
+        CU_TRY(h, cudaEventRecord(h->ev_t1, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
     CU_TRY(h, cudaGetLastError());
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
@@ -507,8 +530,8 @@ int b2ip_create(int d, int device, b2ip_handle* out) {
 int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     if (!out) return fail(nullptr, B2IP_ERR_INVALID, "out is NULL");
     *out = nullptr;
-    if (store_dtype != B2IP_STORE_F32 && store_dtype != B2IP_STORE_BF16)
-        return fail(nullptr, B2IP_ERR_INVALID, "store_dtype=%d: use B2IP_STORE_F32 or B2IP_STORE_BF16", store_dtype);
+    if (store_dtype != B2IP_STORE_F32 && store_dtype != B2IP_STORE_BF16 && store_dtype != B2IP_STORE_F16)
+        return fail(nullptr, B2IP_ERR_INVALID, "store_dtype=%d: use B2IP_STORE_F32, B2IP_STORE_F16 or B2IP_STORE_BF16", store_dtype);
     if (d <= 0 || d % 4 != 0 || d > 4096)
         return fail(nullptr, B2IP_ERR_INVALID, "d=%d: dimension must be a multiple of 4 in [4,4096]", d);
     int ndev = 0;
@@ -529,7 +552,10 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
                     prop.major, prop.minor);
     b2ip_handle h = new b2ip_index_s();
     h->d = d;
-    h->store_bf16 = store_dtype == B2IP_STORE_BF16;
+    h->store16 = store_dtype != B2IP_STORE_F32;
+    h->sh = store_dtype == B2IP_STORE_F16 ? SH_F16 : (store_dtype == B2IP_STORE_BF16 ? SH_BF16 : SH_DEFAULT_F32_STORE);
+    if (store_dtype == B2IP_STORE_F32)
+        if (const char* s = getenv("B2IP_SHADOW")) h->sh = (s[0] == 'f' || s[0] == 'F') ? SH_F16 : SH_BF16;
     h->d_pad = (d + KBLOCK_ELEMS - 1) / KBLOCK_ELEMS * KBLOCK_ELEMS;
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
@@ -600,6 +626,12 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "verbose") h->verbose = static_cast<int>(value);
     else if (n == "pair") h->pair = static_cast<int>(value);
     else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;
+    else if (n == "shadow_f16") {
+        // operand type of the coarse pass of an fp32-stored index; only before the first row
+        if (h->store16) return fail(h, B2IP_ERR_INVALID, "shadow_f16: a 16-bit store fixes the operand type");
+        if (h->n > 0) return fail(h, B2IP_ERR_INVALID, "shadow_f16: set before the first b2ip_add");
+        h->sh = value ? SH_F16 : SH_BF16;
+    }
     else return fail(h, B2IP_ERR_INVALID, "b2ip_set_option: unknown option '%s'", name);
     return B2IP_OK;
 }
@@ -618,35 +650,39 @@ int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem)
     if (src_dtype != B2IP_F32 && src_dtype != B2IP_F16 && src_dtype != B2IP_BF16)
         return fail(h, B2IP_ERR_INVALID, "b2ip_add: src_dtype=%d", src_dtype);
     if (mem != B2IP_MEM_HOST && mem != B2IP_MEM_DEVICE) return fail(h, B2IP_ERR_INVALID, "b2ip_add: mem=%d", mem);
-    if (src_dtype == B2IP_BF16 && !h->store_bf16)
+    if (src_dtype == B2IP_BF16 && !(h->store16 && h->sh == SH_BF16))
         return fail(h, B2IP_ERR_INVALID, "b2ip_add: bf16 rows need an index created with B2IP_STORE_BF16");
+    // rows handed in in the storage type itself are copied as they are
+    const bool same16 = h->store16 && ((src_dtype == B2IP_BF16 && h->sh == SH_BF16) ||
+                                       (src_dtype == B2IP_F16 && h->sh == SH_F16));
     if (n == 0) return B2IP_OK;
     if (h->n + n >= (1ll << 31) - 512) return fail(h, B2IP_ERR_UNSUPPORTED, "a shard holds at most 2^31-512 rows (TMA coordinates are int32)");
     Guard g(h->device);
     RC_TRY(grow_rows(h, h->n + n));
     const cudaMemcpyKind kind = mem == B2IP_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     const int rgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 16));
-    // bf16 storage ingests in bounded chunks through a staging buffer (there is no fp32 master)
-    const int64_t chunk = h->store_bf16 ? std::min<int64_t>(n, 1 << 18) : n;
+    // 16-bit storage ingests in bounded chunks through a staging buffer (there is no fp32 master)
+    const int64_t chunk = h->store16 ? std::min<int64_t>(n, 1 << 18) : n;
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t cn = std::min<int64_t>(chunk, n - c0);
         const size_t count = static_cast<size_t>(cn) * h->d;
         const int64_t r0 = h->n + c0;
-        if (src_dtype == B2IP_BF16) {
+        if (same16) {
             const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(rows) + static_cast<size_t>(c0) * h->d;
             if (mem == B2IP_MEM_HOST) {
                 RC_TRY(ensure(h, h->stage, count * 2));
                 CU_TRY(h, cudaMemcpyAsync(h->stage.p, src, count * 2, kind, h->stream));
                 src = static_cast<const __nv_bfloat16*>(h->stage.p);
             }
-            ingest_bf16_rows_kernel<<<rgrid, 256, 0, h->stream>>>(src, h->x16, r0, r0 + cn, h->d, h->d_pad,
-                                                                  h->norm_stats);
+            ingest_16bit_rows_kernel<<<rgrid, 256, 0, h->stream>>>(src, h->x16, r0, r0 + cn, h->d, h->d_pad,
+                                                                   h->norm_stats, h->sh);
+            if (mem == B2IP_MEM_HOST) CU_TRY(h, cudaStreamSynchronize(h->stream));   // staging buffer is reused
             continue;
         }
         // fp32 destination of this chunk: the master rows, or a staging area (bf16 storage)
         float* dst32;
         size_t f16_off = 0;
-        if (h->store_bf16) {
+        if (h->store16) {
             f16_off = count * sizeof(float);
             RC_TRY(ensure(h, h->stage, f16_off + (src_dtype == B2IP_F16 && mem == B2IP_MEM_HOST ? count * 2 : 0)));
             dst32 = static_cast<float*>(h->stage.p);
@@ -656,7 +692,7 @@ int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem)
         }
         if (src_dtype == B2IP_F32) {
             const float* src = static_cast<const float*>(rows) + static_cast<size_t>(c0) * h->d;
-            if (h->store_bf16 && mem == B2IP_MEM_DEVICE) dst32 = const_cast<float*>(src);   // convert in place from the caller's buffer
+            if (h->store16 && mem == B2IP_MEM_DEVICE) dst32 = const_cast<float*>(src);   // convert in place from the caller's buffer
             else CU_TRY(h, cudaMemcpyAsync(dst32, src, count * sizeof(float), kind, h->stream));
         } else {
             const __half* src = static_cast<const __half*>(rows) + static_cast<size_t>(c0) * h->d;
@@ -669,8 +705,8 @@ int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem)
             widen_f16_kernel<<<grid, 256, 0, h->stream>>>(src, dst32, static_cast<long long>(count));
         }
         shadow_rows_kernel<<<rgrid, 256, 0, h->stream>>>(dst32, r0, h->x16, r0, r0 + cn, h->d, h->d_pad,
-                                                         h->norm_stats, !h->store_bf16);
-        if (h->store_bf16) CU_TRY(h, cudaStreamSynchronize(h->stream));   // staging buffer is reused
+                                                         h->norm_stats, !h->store16, h->sh);
+        if (h->store16) CU_TRY(h, cudaStreamSynchronize(h->stream));   // staging buffer is reused
     }
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -746,13 +782,13 @@ int b2ip_export_rows(b2ip_handle h, int64_t row0, int64_t n, float* out, int mem
     if (n == 0) return B2IP_OK;
     Guard g(h->device);
     const float* src = h->x32 ? h->x32 + row0 * h->d : nullptr;
-    if (h->store_bf16) {
+    if (h->store16) {
         float* tmp = out;
         if (mem == B2IP_MEM_HOST) {
             RC_TRY(ensure(h, h->stage, static_cast<size_t>(n) * h->d * sizeof(float)));
             tmp = static_cast<float*>(h->stage.p);
         }
-        widen_bf16_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(h->x16, row0, n, h->d, h->d_pad, tmp);
+        widen_16bit_rows_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(h->x16, row0, n, h->d, h->d_pad, tmp, h->sh);
         if (mem == B2IP_MEM_DEVICE) { CU_TRY(h, cudaStreamSynchronize(h->stream)); return B2IP_OK; }
         src = tmp;
     }
@@ -776,7 +812,7 @@ int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev
         return fail(h, B2IP_ERR_INVALID, "b2ip_debug_coarse_scores: bad arguments");
     if (row0 % TILE_X != 0) return fail(h, B2IP_ERR_INVALID, "row0 must be a multiple of %d", TILE_X);
     Guard g(h->device);
-    RC_TRY(ensure(h, h->q16, static_cast<size_t>(nq) * h->d_pad * 2));
+    RC_TRY(ensure(h, h->q16, static_cast<size_t>(pad_q(nq)) * h->d_pad * 2));
     RC_TRY(ensure(h, h->eps2, nq * sizeof(float)));
     RC_TRY(ensure(h, h->thr, nq * sizeof(float)));
     RC_TRY(ensure(h, h->cnt, nq * sizeof(int)));
@@ -785,9 +821,12 @@ int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev
     prep_queries_kernel<<<static_cast<int>((nq + 7) / 8), 256, 0, h->stream>>>(
         queries_dev, reinterpret_cast<__nv_bfloat16*>(h->q16.p), static_cast<int>(nq), h->d, h->d_pad,
         h->norm_stats, reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
-        reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p), reinterpret_cast<int*>(h->flags.p));
+        reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p), reinterpret_cast<int*>(h->flags.p), h->sh);
+    if (pad_q(nq) > nq)
+        CU_TRY(h, cudaMemsetAsync(static_cast<char*>(h->q16.p) + static_cast<size_t>(nq) * h->d_pad * 2, 0,
+                                  static_cast<size_t>(pad_q(nq) - nq) * h->d_pad * 2, h->stream));
     CUtensorMap tmap_q, tmap_x;
-    RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, nq, h->d_pad, TILE_Q));
+    RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nq), h->d_pad, TILE_Q));
     RC_TRY(make_tmap_bf16(h, &tmap_x, h->x16, h->n, h->d_pad, TILE_X));
     CU_TRY(h, cudaFuncSetAttribute(coarse_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    COARSE_SMEM_BYTES));
@@ -804,6 +843,7 @@ int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev
     cp.dump_ld = n_rows;
     cp.hint_q = hint_policy(h->hint_q);
     cp.hint_x = hint_policy(h->hint_x);
+    cp.idesc = IDESC_SINGLE[h->sh];
     const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
     const int grid = static_cast<int>(std::min<long long>(tiles, h->sm_count));
     coarse_filter_kernel<true><<<grid, COARSE_THREADS, COARSE_SMEM_BYTES, h->stream>>>(tmap_q, tmap_x, cp);

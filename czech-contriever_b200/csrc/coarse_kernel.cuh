@@ -37,7 +37,11 @@ constexpr int HIT_STAGE_BYTES = HIT_SLOTS * 128 * 8;
 constexpr int COARSE_SMEM_BYTES =
     STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + HIT_STAGE_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t IDESC_BF16 = ptx::umma_idesc(/*bf16*/ 1, TILE_Q, TILE_X);
+// tcgen05 instruction descriptors, indexed by the operand format (SH_BF16 = 0, SH_F16 = 1)
+constexpr uint32_t IDESC_SINGLE[2] = {ptx::umma_idesc(/*bf16*/ 1, TILE_Q, TILE_X),
+                                      ptx::umma_idesc(/*f16*/ 0, TILE_Q, TILE_X)};
+constexpr uint32_t IDESC_PAIR[2] = {ptx::umma_idesc(/*bf16*/ 1, 256, TILE_X),
+                                    ptx::umma_idesc(/*f16*/ 0, 256, TILE_X)};
 
 struct CoarseParams {
     int num_k_blocks;        // d_pad / 64
@@ -54,6 +58,7 @@ struct CoarseParams {
     float* dump;             // debug: [nq, dump_ld] raw scores, or nullptr
     long long dump_ld;
     unsigned long long hint_q, hint_x;   // L2 eviction-priority policies of the two TMA streams
+    uint32_t idesc;          // tcgen05 instruction descriptor (IDESC_SINGLE / IDESC_PAIR [format])
     int dbg;                 // perf experiments only (results are wrong when set):
                              // 1 = every tile loads corpus tile 0, 2 = no TMA loads, 4 = no filter
 };
@@ -230,7 +235,7 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     for (int k = 0; k < KBLOCK_BYTES / UMMA_K_BYTES; k++) {
                         const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr + k * UMMA_K_BYTES);
                         const uint64_t bdesc = ptx::umma_desc_k_sw128(b_addr + k * UMMA_K_BYTES);
-                        ptx::mma_f16_ss(d_tmem, adesc, bdesc, IDESC_BF16, (kb | k) != 0);
+                        ptx::mma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (kb | k) != 0);
                     }
                     ptx::tc_commit(&empty_bar[stage]);   // smem slot reusable once MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -313,7 +318,6 @@ constexpr int PAIR_HALF_BYTES = 128 * KBLOCK_BYTES;            // 16 KiB: 128 ro
 constexpr int PAIR_STAGE_BYTES = 2 * PAIR_HALF_BYTES;          // A half + B half per CTA
 constexpr int PAIR_SMEM_BYTES =
     PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256 + HIT_STAGE_BYTES;
-constexpr uint32_t IDESC_BF16_PAIR = ptx::umma_idesc(/*bf16*/ 1, 256, TILE_X);
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(COARSE_THREADS, 1)
 coarse_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -404,7 +408,7 @@ coarse_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     for (int k = 0; k < KBLOCK_BYTES / UMMA_K_BYTES; k++) {
                         const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr + k * UMMA_K_BYTES);
                         const uint64_t bdesc = ptx::umma_desc_k_sw128(b_addr + k * UMMA_K_BYTES);
-                        ptx::mma_f16_ss_pair(d_tmem, adesc, bdesc, IDESC_BF16_PAIR, (kb | k) != 0);
+                        ptx::mma_f16_ss_pair(d_tmem, adesc, bdesc, p.idesc, (kb | k) != 0);
                     }
                     ptx::tc_commit_pair(&empty_bar[stage], 0x3);
                     if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }

@@ -35,6 +35,32 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------
+// 16-bit operand formats of the coarse GEMM ("shadow" rows / queries)
+// ---------------------------------------------------------------------------------------
+// SH_BF16: 8 exponent bits, never overflows for fp32 inputs below 3.39e38.
+// SH_F16 : 3 more mantissa bits (an 8x tighter error bound on normalised embeddings, and
+//          LOSSLESS for the reference's default fp16 embedding shards); values are saturated to
+//          +-65504 so the shadow never holds an infinity the input did not have -- the error
+//          bound is computed from the value actually stored, so saturation only loosens it.
+enum { SH_BF16 = 0, SH_F16 = 1 };
+
+__device__ __forceinline__ float sat_f16(float v) {
+    return (v != v) ? v : fminf(fmaxf(v, -65504.f), 65504.f);      // NaN stays NaN
+}
+__device__ __forceinline__ uint32_t pack2_sh(float a, float b, int sh) {
+    if (sh == SH_F16) {
+        const __half2 h = __floats2half2_rn(sat_f16(a), sat_f16(b));
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2_sh(uint32_t raw, int sh) {
+    if (sh == SH_F16) return __half22float2(*reinterpret_cast<const __half2*>(&raw));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
+}
+
+// ---------------------------------------------------------------------------------------
 // corpus ingest
 // ---------------------------------------------------------------------------------------
 __global__ void widen_f16_kernel(const __half* __restrict__ src, float* __restrict__ dst,
@@ -48,15 +74,15 @@ __global__ void widen_f16_kernel(const __half* __restrict__ src, float* __restri
     if (i < count && i + 1 >= count) dst[i] = __half2float(src[i]);
 }
 
-// One warp per row: bf16 shadow (zero padded to d_pad) + max ||x||^2 and max ||x - bf16(x)||^2
+// One warp per row: 16-bit shadow (zero padded to d_pad) + max ||x||^2 and max ||x - sh(x)||^2
 // over all rows, which feed the per-query error bound of the coarse scores.
 // `src` points at the fp32 rows of [row0,row1) (src_row0 = index of its first row): the master
-// rows themselves (fp32 storage) or a staging chunk (bf16 storage, count_delta = false: the
-// stored value IS the bf16 one, so x - bf(x) is zero by definition).
+// rows themselves (fp32 storage) or a staging chunk (16-bit storage, count_delta = false: the
+// stored value IS the rounded one, so x - sh(x) is zero by definition).
 __global__ void shadow_rows_kernel(const float* __restrict__ src, long long src_row0,
                                    __nv_bfloat16* __restrict__ x16,
                                    long long row0, long long row1, int d, int d_pad,
-                                   unsigned int* __restrict__ norm_stats, bool count_delta) {
+                                   unsigned int* __restrict__ norm_stats, bool count_delta, int sh) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -68,16 +94,14 @@ __global__ void shadow_rows_kernel(const float* __restrict__ src, long long src_
         for (int j = lane; j < d_pad / 4; j += 32) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < d / 4) v = __ldg(srow + j);
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
-            const float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);
+            uint2 o;
+            o.x = pack2_sh(v.x, v.y, sh);
+            o.y = pack2_sh(v.z, v.w, sh);
+            const float2 flo = unpack2_sh(o.x, sh), fhi = unpack2_sh(o.y, sh);
             const float e0 = v.x - flo.x, e1 = v.y - flo.y, e2 = v.z - fhi.x, e3 = v.w - fhi.y;
             if (!count_delta) v = make_float4(flo.x, flo.y, fhi.x, fhi.y);
             nx += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
             nd += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
-            uint2 o;
-            o.x = *reinterpret_cast<const unsigned int*>(&lo);
-            o.y = *reinterpret_cast<const unsigned int*>(&hi);
             dst[j] = o;
         }
         nx = warp_sum(nx);
@@ -92,23 +116,24 @@ __global__ void shadow_rows_kernel(const float* __restrict__ src, long long src_
     }
 }
 
-// bf16 rows handed in as bf16: copy into the padded layout + max ||x||^2.  One warp per row.
-__global__ void ingest_bf16_rows_kernel(const __nv_bfloat16* __restrict__ src,
-                                        __nv_bfloat16* __restrict__ x16, long long row0,
-                                        long long row1, int d, int d_pad,
-                                        unsigned int* __restrict__ norm_stats) {
+// 16-bit rows handed in in the storage type itself (bf16 -> bf16 store, fp16 -> fp16 store):
+// copy into the padded layout + max ||x||^2.  One warp per row.
+__global__ void ingest_16bit_rows_kernel(const __nv_bfloat16* __restrict__ src,
+                                         __nv_bfloat16* __restrict__ x16, long long row0,
+                                         long long row1, int d, int d_pad,
+                                         unsigned int* __restrict__ norm_stats, int sh) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     float mx = 0.f;
     for (long long r = row0 + warp; r < row1; r += nwarps) {
-        const __nv_bfloat162* srow = reinterpret_cast<const __nv_bfloat162*>(src + (r - row0) * d);
-        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(x16 + r * d_pad);
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(src + (r - row0) * d);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(x16 + r * d_pad);
         float nx = 0.f;
         for (int j = lane; j < d_pad / 2; j += 32) {
-            __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+            uint32_t v = 0u;
             if (j < d / 2) v = srow[j];
-            const float2 f = __bfloat1622float2(v);
+            const float2 f = unpack2_sh(v, sh);
             nx += f.x * f.x + f.y * f.y;
             dst[j] = v;
         }
@@ -118,40 +143,42 @@ __global__ void ingest_bf16_rows_kernel(const __nv_bfloat16* __restrict__ src,
     if (lane == 0) atomicMax(norm_stats + 0, __float_as_uint(mx));
 }
 
-__global__ void widen_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x16, long long row0,
-                                       long long n, int d, int d_pad, float* __restrict__ out) {
+__global__ void widen_16bit_rows_kernel(const __nv_bfloat16* __restrict__ x16, long long row0,
+                                        long long n, int d, int d_pad, float* __restrict__ out,
+                                        int sh) {
     const long long total = n * d;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = i / d;
         const int j = static_cast<int>(i - r * d);
-        out[i] = __bfloat162float(x16[(row0 + r) * d_pad + j]);
+        const unsigned short raw = reinterpret_cast<const unsigned short*>(x16)[(row0 + r) * d_pad + j];
+        out[i] = unpack2_sh(raw, sh).x;
     }
 }
 
 // One corpus row as 4 consecutive floats starting at element 4*j4, from either storage.
 __device__ __forceinline__ float4 load_row4(const float* __restrict__ x32,
                                             const __nv_bfloat16* __restrict__ x16, long long row,
-                                            int d, int d_pad, int j4) {
+                                            int d, int d_pad, int j4, int sh) {
     if (x32) return __ldg(reinterpret_cast<const float4*>(x32 + row * d) + j4);
     const uint2 raw = __ldg(reinterpret_cast<const uint2*>(x16 + row * d_pad) + j4);
-    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-    const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    const float2 lo = unpack2_sh(raw.x, sh), hi = unpack2_sh(raw.y, sh);
     return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // ---------------------------------------------------------------------------------------
-// query preparation: bf16 copy + eps2[q] = 2 * bound(|coarse - exact|), state reset
+// query preparation: 16-bit copy + eps2[q] = 2 * bound(|coarse - exact|), state reset
 // ---------------------------------------------------------------------------------------
-// |q.x - bf(q).bf(x)| = |bf(q).(x - bf(x)) + (q - bf(q)).x|
-//                    <= ||bf(q)|| * max||x - bf(x)|| + ||q - bf(q)|| * max||x||      (Cauchy-Schwarz)
-// plus a slack for the tensor core's fp32 accumulation: d_pad * 2^-23 * ||bf(q)|| * max||bf(x)||.
+// with sh() the rounding to the operand type (bf16 or saturated fp16):
+// |q.x - sh(q).sh(x)| = |sh(q).(x - sh(x)) + (q - sh(q)).x|
+//                    <= ||sh(q)|| * max||x - sh(x)|| + ||q - sh(q)|| * max||x||      (Cauchy-Schwarz)
+// plus a slack for the tensor core's fp32 accumulation: d_pad * 2^-23 * ||sh(q)|| * max||sh(x)||.
 __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16* __restrict__ q16,
                                     int nq, int d, int d_pad,
                                     const unsigned int* __restrict__ norm_stats,
                                     float* __restrict__ eps2, float* __restrict__ thr,
                                     int* __restrict__ cnt, int* __restrict__ kept,
-                                    int* __restrict__ flags) {
+                                    int* __restrict__ flags, int sh) {
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
@@ -161,15 +188,13 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
     for (int j = lane; j < d_pad / 4; j += 32) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < d / 4) v = __ldg(src + j);
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
-        const float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);
+        uint2 o;
+        o.x = pack2_sh(v.x, v.y, sh);
+        o.y = pack2_sh(v.z, v.w, sh);
+        const float2 flo = unpack2_sh(o.x, sh), fhi = unpack2_sh(o.y, sh);
         const float e0 = v.x - flo.x, e1 = v.y - flo.y, e2 = v.z - fhi.x, e3 = v.w - fhi.y;
         nh += flo.x * flo.x + flo.y * flo.y + fhi.x * fhi.x + fhi.y * fhi.y;
         nd += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
-        uint2 o;
-        o.x = *reinterpret_cast<const unsigned int*>(&lo);
-        o.y = *reinterpret_cast<const unsigned int*>(&hi);
         dst[j] = o;
     }
     nh = warp_sum(nh);
@@ -401,8 +426,9 @@ struct FinalizeParams {
     const int* flags;                 // [slots] or nullptr
     const float* q32;                 // [*, d] fp32 queries (rescore)
     const float* x32;                 // [n, d] fp32 corpus (rescore), or nullptr:
-    const __nv_bfloat16* x16;         // [n, d_pad] bf16 corpus when the index stores bf16
+    const __nv_bfloat16* x16;         // [n, d_pad] 16-bit corpus when the index stores bf16 / fp16
     int d_pad;
+    int sh;                           // SH_BF16 / SH_F16: element type of x16
     long long row_offset;
     float* out_scores;                // [*, k]
     long long* out_rows;              // [*, k]
@@ -455,8 +481,8 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
             const uint32_t row2 = has2 ? key_row(keys[i2]) : row;
             double acc = 0.0, acc2 = 0.0;
             for (int j = lane; j < p.d / 4; j += 32) {
-                const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j);
-                const float4 a2 = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j);
+                const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j, p.sh);
+                const float4 a2 = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j, p.sh);
                 const float4 b = q4[j];
                 acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
                 acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
@@ -512,7 +538,7 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 exact_scores_kernel(const float* __restrict__ x32, const __nv_bfloat16* __restrict__ x16,
-                    long long n, int d, int d_pad, const float* __restrict__ q32, const int* __restrict__ qlist, int nqg,
+                    long long n, int d, int d_pad, int sh, const float* __restrict__ q32, const int* __restrict__ qlist, int nqg,
                     float* __restrict__ scores /*[EXACT_QB, n]*/) {
     extern __shared__ __align__(16) float esq[];   // [EXACT_QB, d]
     for (int i = threadIdx.x; i < EXACT_QB * d; i += blockDim.x) {
@@ -530,7 +556,7 @@ exact_scores_kernel(const float* __restrict__ x32, const __nv_bfloat16* __restri
 #pragma unroll
         for (int b = 0; b < EXACT_QB; b++) acc[b] = 0.f;
         for (int j = lane; j < d4; j += 32) {
-            const float4 xv = load_row4(x32, x16, r, d, d_pad, j);
+            const float4 xv = load_row4(x32, x16, r, d, d_pad, j, sh);
 #pragma unroll
             for (int b = 0; b < EXACT_QB; b++) {
                 const float4 qv = sq4[b * d4 + j];

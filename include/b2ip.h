@@ -40,7 +40,12 @@ enum {
 enum { B2IP_F32 = 0, B2IP_F16 = 1, B2IP_BF16 = 2 };   /* element type of rows handed to b2ip_add */
 /* how the index keeps its rows in HBM */
 enum {
-    B2IP_STORE_F32 = 0,  /* fp32 master rows (+ a bf16 shadow for the coarse pass): faiss semantics  */
+    B2IP_STORE_F32 = 0,  /* fp32 master rows (+ a 16-bit shadow for the coarse pass): faiss semantics */
+    B2IP_STORE_F16 = 1,  /* rows ARE fp16: LOSSLESS for the reference's default pipeline, whose
+                            embedding shards are float16 (generate_passage_embeddings.py:75-76)
+                            and only widened by astype('float32') (src/index.py:27); fp32 rows
+                            are rounded to nearest (saturating) at ingest.  A third of the
+                            memory of B2IP_STORE_F32, same results on fp16-valued rows.        */
     B2IP_STORE_BF16 = 2  /* rows ARE bf16 (rounded to nearest at ingest unless given as bf16); the
                             search is exact w.r.t. those stored values, rescored in fp32 (BASELINE
                             config 4).  Half the memory, no shadow copy.                        */
@@ -91,7 +96,9 @@ int b2ip_set_stream(b2ip_handle h, void* cuda_stream);
 
 /* Tuning knobs (all have working defaults): "gx" x-tiles per raster group, "hint_q"/"hint_x"
  * L2 eviction priority of the query / corpus TMA streams (0 normal, 1 first, 2 last),
- * "cand_budget_mb" device memory allowed for candidate lists (sets the query batch). */
+ * "cand_budget_mb" device memory allowed for candidate lists (sets the query batch),
+ * "shadow_f16" (B2IP_STORE_F32 only, before the first add): 1 = fp16 operands for the coarse
+ * pass instead of bf16 (tighter error bound, saturating at +-65504), "pair" 0/1 CTA-pair kernel. */
 int b2ip_set_option(b2ip_handle h, const char* name, int64_t value);
 
 /* Optional capacity hint before a series of b2ip_add calls (avoids regrowth copies). */

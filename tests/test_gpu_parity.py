@@ -237,6 +237,109 @@ def test_bf16_storage_fp16_host_rows_and_rejects_bf16_on_f32_index(fo):
         check(f32._lib.b2ip_add(f32._h, 4, ctypes.c_void_p(t.data_ptr()), B2IP_BF16, MEM_DEVICE), f32._h)
 
 
+@pytest.mark.parametrize("mode", ["tensor", "exact"])
+@pytest.mark.parametrize("k", [10, 100, 1000])
+def test_f16_storage_is_lossless_for_fp16_shards(fo, mode, k):
+    """The reference's default pipeline: float16 shards, widened by astype('float32')
+    (src/index.py:27).  An fp16 store keeps exactly those values: the oracle sees x.astype(f32)."""
+    import torch
+    from b2ip import Engine
+    x = (synth(30000, 768, 71, normalize=False) * 0.3).astype(np.float16)
+    q = (synth(48, 768, 72, normalize=False) * 0.3).astype(np.float16).astype(np.float32)
+    e = Engine(768, 0, store="f16")
+    e.add(x[:10000])                                             # fp16 host rows
+    e.add(torch.from_numpy(x[10000:20000]).cuda())               # fp16 device rows
+    e.add(torch.from_numpy(x[20000:].astype(np.float32)).cuda())  # fp32 rows that are fp16-valued
+    x32 = x.astype(np.float32)
+    np.testing.assert_array_equal(e.export_rows(9990, 20), x32[9990:10010])
+    np.testing.assert_array_equal(e.export_rows(19990, 20), x32[19990:20010])
+    D, I = e.search(q, k, mode=mode)
+    Do, Io = fo.search(q, x32, k)
+    fo.compare_topk(D, I, Do, Io, q, x32, rtol=RTOL)
+    st = e.stats()
+    assert st["fallback_queries"] == 0
+    if mode == "tensor":
+        # lossless operands: the error bound is accumulation slack only, so little more than
+        # the top-k itself survives to the rescore
+        assert st["rescored"] <= 48 * (k + k // 10 + 8)
+
+
+def test_f16_storage_rounds_fp32_rows_and_saturates(fo):
+    """fp32 rows into an fp16 store are rounded to nearest, saturating at +-65504 (no inf is
+    ever created); the search is exact on the stored values."""
+    from b2ip import Engine
+    x = synth(6000, 256, 73, normalize=False)
+    x[17, 3] = 1.0e6
+    x[18, 5] = -3.0e7
+    e = Engine(256, 0, store="f16")
+    e.add(x)
+    xr = np.clip(x, -65504.0, 65504.0).astype(np.float16).astype(np.float32)
+    np.testing.assert_array_equal(e.export_rows(0, 6000), xr)
+    q = synth(20, 256, 74)
+    D, I = e.search(q, 50)
+    Do, Io = fo.search(q, xr, 50)
+    fo.compare_topk(D, I, Do, Io, q, xr, rtol=RTOL)
+
+
+@pytest.mark.parametrize("shadow", ["bf16", "f16"])
+def test_shadow_operand_type_of_an_fp32_index(fo, shadow):
+    """fp32 master rows with either 16-bit operand type for the coarse pass: same answers; the
+    fp16 shadow's tighter bound sends fewer rows to the rescore.  Includes values beyond the
+    fp16 range (saturated shadow, bound computed from the stored value)."""
+    from b2ip import Engine
+    x = synth(40000, 768, 81)
+    q = synth(64, 768, 82)
+    e = Engine(768, 0, shadow=shadow)
+    e.add(x)
+    D, I = e.search(q, 100, mode="tensor")
+    Do, Io = fo.search(q, x, 100)
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+    st = e.stats()
+    assert st["fallback_queries"] == 0
+    resc = st["rescored"] / 64
+    assert resc < (140 if shadow == "f16" else 400), resc
+    if shadow == "f16":
+        got = e.debug_coarse_scores(__import__("torch").from_numpy(q).cuda(), 0, 1024).cpu().numpy()
+        want = q.astype(np.float16).astype(np.float64) @ x[:1024].astype(np.float16).astype(np.float64).T
+        np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
+    # out-of-range values: still exact (the affected queries may take the exact path)
+    x2 = x[:5000].copy()
+    x2[100] *= 1.0e6
+    e2 = Engine(768, 0, shadow=shadow)
+    e2.add(x2)
+    D, I = e2.search(q[:8], 10)
+    Do, Io = fo.search(q[:8], x2, 10)
+    fo.compare_topk(D, I, Do, Io, q[:8], x2, rtol=RTOL)
+
+
+def test_indexer_auto_store_and_migration(fo):
+    """Indexer(store='auto'): float16 chunks live in an fp16 store; the first non-fp16 chunk moves
+    everything to fp32 master rows.  Results equal the reference restatement either way."""
+    from src.index import Indexer
+    d, k = 256, 20
+    a = (synth(3000, d, 91, normalize=False) * 0.5).astype(np.float16)
+    b = (synth(2000, d, 92, normalize=False) * 0.5).astype(np.float16)
+    c = synth(1000, d, 93, normalize=False) * 0.5                       # fp32, not fp16-valued
+    ours, ref = Indexer(d, 0, 8), fo.OracleIndexer(d, 0, 8)
+    for idx in (ours, ref):
+        idx.index_data([str(i) for i in range(3000)], a)
+        idx.index_data([str(3000 + i) for i in range(2000)], b)
+    assert ours.index.store == "f16" and ours.index.ntotal == 5000
+    q = (synth(30, d, 94, normalize=False)).astype(np.float16)
+
+    def check():
+        got, want = ours.search_knn(q, k), ref.search_knn(q, k)
+        fo.compare_topk(np.stack([g[1] for g in got]), np.array([[int(s) for s in g[0]] for g in got]),
+                        np.stack([w[1] for w in want]), np.array([[int(s) for s in w[0]] for w in want]),
+                        q.astype(np.float32), ref.rows, rtol=RTOL)
+    check()
+    for idx in (ours, ref):
+        idx.index_data([str(5000 + i) for i in range(1000)], c)
+    assert ours.index.store == "f32" and ours.index.ntotal == 6000
+    np.testing.assert_array_equal(ours.index.export_rows(2990, 20), np.concatenate([a, b])[2990:3010].astype(np.float32))
+    check()
+
+
 def test_incremental_adds_equal_one_add(fo):
     x = synth(7000, 768, 21)
     q = synth(20, 768, 22)

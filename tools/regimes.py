@@ -12,13 +12,14 @@ ap.add_argument("--d", type=int, default=768)
 ap.add_argument("--cases", default="100000:100,100000:1000,10000:100,1:10,4:10,16:10,64:10,256:10,2048:100")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--store", default="f32")
+ap.add_argument("--shadow", default=None, help="bf16 | f16 (store=f32 only)")
 ap.add_argument("--verbose", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 
 
 def build(n):
-    e = Engine(a.d, 0, store=a.store)
+    e = Engine(a.d, 0, store=a.store, shadow=a.shadow)
     e.reserve(n)
     CH = 1 << 18
     for c0 in range(0, n, CH):
@@ -49,7 +50,7 @@ for case in a.cases.split(","):
         if w < best_wall:
             best_wall, best = w, e.stats()
     flops = 2.0 * nq * a.n_corpus * a.d
-    print(json.dumps({"n": a.n_corpus, "nq": nq, "k": k, "wall_ms": round(best_wall, 3),
+    print(json.dumps({"store": a.store, "shadow": a.shadow, "n": a.n_corpus, "nq": nq, "k": k, "wall_ms": round(best_wall, 3),
                       "dev_ms": round(best["total_ms"], 3), "coarse_ms": round(best["coarse_ms"], 3), "refresh_ms": round(best["refresh_ms"], 3), "finalize_ms": round(best["finalize_ms"], 3),
                       "tflops_wall": round(flops / best_wall / 1e9, 1), "hbm_floor_ms_bf16": round(hbm_ms, 3),
                       "qps": round(nq / best_wall * 1e3, 1), "slabs": best["slabs"], "launches": best["total_launches"],
