@@ -164,17 +164,23 @@ class Engine:
 
 
 def merge_topk(scores, rows, k: int):
-    """Device merge of per-shard results: scores/rows torch CUDA tensors [G,nq,k] -> ([nq,k],[nq,k])."""
+    """Device merge of per-shard results: scores/rows torch CUDA tensors [G,nq,k] -> ([nq,k],[nq,k]).
+    The G lists may be strided views (e.g. slices of one packed all-gather buffer) as long as
+    each [nq,k] list is itself contiguous."""
     import torch
     lib = _lib.load()
     G, nq, kk = scores.shape
     assert kk == k and rows.shape == scores.shape
-    scores = scores.contiguous()
-    rows = rows.contiguous()
+    if not scores[0].is_contiguous() or (G > 1 and scores.stride(0) < nq * k):
+        scores = scores.contiguous()
+    if not rows[0].is_contiguous() or (G > 1 and rows.stride(0) < nq * k):
+        rows = rows.contiguous()
     D = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
     I = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
     stream = torch.cuda.current_stream(scores.device)
-    check(lib.b2ip_merge_topk(scores.device.index, ctypes.c_void_p(stream.cuda_stream), nq, k, G,
-                              ctypes.c_void_p(scores.data_ptr()), ctypes.c_void_p(rows.data_ptr()),
-                              ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr())), None)
+    check(lib.b2ip_merge_topk_strided(
+        scores.device.index, ctypes.c_void_p(stream.cuda_stream), nq, k, G,
+        ctypes.c_void_p(scores.data_ptr()), ctypes.c_void_p(rows.data_ptr()),
+        scores.stride(0) if G > 1 else nq * k, rows.stride(0) if G > 1 else nq * k,
+        ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr())), None)
     return D, I

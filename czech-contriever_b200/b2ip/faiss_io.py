@@ -6,7 +6,8 @@ published format -- no faiss is installable here to cross-check):
     fourcc "IxFI" | int32 d | int64 ntotal | int64 dummy=1<<20 | int64 dummy=1<<20 |
     uint8 is_trained | int32 metric_type (0 = METRIC_INNER_PRODUCT) |
     uint64 count = ntotal*d | float32[count] row-major
-Rows are streamed in chunks so a 64 GB index never needs a second host copy.
+Rows are streamed in chunks so a 64 GB index never needs a second host copy, and the file
+I/O runs one chunk ahead of / behind the GPU copies on a background thread.
 """
 from __future__ import annotations
 
@@ -22,12 +23,17 @@ _CHUNK_ROWS = 1 << 18
 def write_flat_ip(path: str, d: int, ntotal: int,
                   export_rows: Callable[[int, int], np.ndarray]) -> None:
     """export_rows(row0, n) -> float32 [n,d] (e.g. Engine.export_rows)."""
+    from .ingest import prefetch
+
+    def chunks():
+        for r0 in range(0, ntotal, _CHUNK_ROWS):
+            yield np.ascontiguousarray(export_rows(r0, min(_CHUNK_ROWS, ntotal - r0)), dtype="<f4")
+
     with open(path, "wb") as f:
         f.write(_HDR.pack(b"IxFI", d, ntotal, 1 << 20, 1 << 20, 1, 0))
         f.write(struct.pack("<Q", ntotal * d))
-        for r0 in range(0, ntotal, _CHUNK_ROWS):
-            n = min(_CHUNK_ROWS, ntotal - r0)
-            f.write(np.ascontiguousarray(export_rows(r0, n), dtype="<f4").tobytes())
+        for block in prefetch(chunks(), depth=1):      # D2H of chunk i+1 overlaps the write of chunk i
+            f.write(memoryview(block).cast("B"))
 
 
 def read_flat_ip_header(f) -> Tuple[int, int]:
@@ -62,4 +68,5 @@ def stream_flat_ip_rows(path: str) -> Tuple[int, int, Iterator[np.ndarray]]:
         finally:
             f.close()
 
-    return d, ntotal, blocks()
+    from .ingest import prefetch
+    return d, ntotal, prefetch(blocks(), depth=2)     # the read of chunk i+1 overlaps the H2D of chunk i

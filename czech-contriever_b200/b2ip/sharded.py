@@ -104,20 +104,38 @@ class ShardedIndex:
 
     def search(self, queries, k: int, mode: str = "auto"):
         """queries: [nq,d] tensor on this rank's device (identical on all ranks).
-        Returns the global (scores [nq,k], rows [nq,k]) on every rank."""
+        Returns the global (scores [nq,k], rows [nq,k]) on every rank.
+
+        One exchange step: every rank owns a slot [rows int64 | scores fp32] of ONE packed
+        buffer, the engine writes its local top-k straight into its slot, a single in-place
+        all-gather fills the others, and the merge kernel reads the slots where they are."""
         torch, dist = self._torch, self._dist
-        D, I = self.search_local(queries, k, mode)
         if self.world == 1:
-            return D, I
-        gD = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
-        gI = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+            return self.search_local(queries, k, mode)
+        nq = int(queries.shape[0])
+        nb = nq * k
+        slot = (nb * 12 + 15) // 16 * 16
+        buf = torch.empty((self.world, slot), dtype=torch.uint8, device=queries.device)
+        mine = buf[self.rank]
+        I_mine = mine[:nb * 8].view(torch.int64).view(nq, k)
+        D_mine = mine[nb * 8:nb * 12].view(torch.float32).view(nq, k)
+        if self._engine_writes_in_place():
+            self.engine.search(queries, k, mode=mode, out=(D_mine, I_mine))
+            Ig = self._to_global(I_mine)
+            if Ig is not I_mine:
+                I_mine.copy_(Ig)
+        else:
+            D, I = self.search_local(queries, k, mode)
+            D_mine.copy_(D)
+            I_mine.copy_(I)
         try:
-            dist.all_gather_into_tensor(gD, D.contiguous(), group=self.group)
-            dist.all_gather_into_tensor(gI, I.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(buf.view(-1), mine, group=self.group)
         except (RuntimeError, NotImplementedError):
-            lD = [torch.empty_like(D) for _ in range(self.world)]
-            lI = [torch.empty_like(I) for _ in range(self.world)]
-            dist.all_gather(lD, D.contiguous(), group=self.group)
-            dist.all_gather(lI, I.contiguous(), group=self.group)
-            gD, gI = torch.stack(lD), torch.stack(lI)
+            dist.all_gather([buf[r] for r in range(self.world)], mine.clone(), group=self.group)
+        gI = buf[:, :nb * 8].view(torch.int64).view(self.world, nq, k)
+        gD = buf[:, nb * 8:nb * 12].view(torch.float32).view(self.world, nq, k)
         return self.merge_fn(gD, gI, k)
+
+    def _engine_writes_in_place(self) -> bool:
+        from .engine import Engine
+        return isinstance(self.engine, Engine)

@@ -18,7 +18,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b2ip.h"
@@ -50,7 +53,13 @@ struct DevBuf {
 
 }  // namespace
 
+namespace { class CopyPool; }
+
 struct b2ip_index_s {
+    void* pin[2] = {nullptr, nullptr};    // pinned staging of host_to_device
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    int pin_next = 0;
+    CopyPool* pool = nullptr;
     int d = 0, d_pad = 0, device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     float* x32 = nullptr;
@@ -75,6 +84,9 @@ struct b2ip_index_s {
     int verbose = 0;
     int pair = 1;                         // CTA-pair (cta_group::2) scoring kernel when nq > 128
     long long cand_budget_bytes = 6ll << 30;
+    CUtensorMap tmap_x, tmap_x_pair;      // cached TMA descriptors of x16 (single / pair box)
+    const void* tmap_x_base = nullptr;
+    int64_t tmap_x_rows = -1;
 };
 
 namespace {
@@ -202,6 +214,129 @@ cudaEvent_t get_event(b2ip_handle h, size_t i) { return get_event(h->ev_pool, i)
 
 int64_t pad_q(int64_t nq) { return (nq + 2 * TILE_Q - 1) / (2 * TILE_Q) * (2 * TILE_Q); }
 
+// ------------------------------------------------------------------------- host -> device staging
+// Worker threads that copy one host range in parallel slices (pageable -> pinned).
+class CopyPool {
+  public:
+    explicit CopyPool(int n) : n_(n) {
+        for (int i = 0; i < n; i++) th_.emplace_back([this, i] { run(i); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void copy(void* dst, const void* src, size_t bytes) {
+        if (n_ == 0 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+        std::unique_lock<std::mutex> l(m_);
+        dst_ = static_cast<char*>(dst); src_ = static_cast<const char*>(src); bytes_ = bytes;
+        left_ = n_; gen_++;
+        cv_.notify_all();
+        done_.wait(l, [this] { return left_ == 0; });
+    }
+  private:
+    void run(int i) {
+        int seen = 0;
+        std::unique_lock<std::mutex> l(m_);
+        for (;;) {
+            cv_.wait(l, [&] { return gen_ != seen; });
+            seen = gen_;
+            if (stop_) return;
+            char* d = dst_; const char* s = src_; const size_t b = bytes_;
+            l.unlock();
+            size_t per = (b + n_ - 1) / n_;
+            per = (per + 4095) & ~static_cast<size_t>(4095);
+            const size_t o = per * static_cast<size_t>(i);
+            if (o < b) memcpy(d + o, s + o, std::min(per, b - o));
+            l.lock();
+            if (--left_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0;
+    int left_ = 0, gen_ = 0;
+    bool stop_ = false;
+};
+
+constexpr size_t PIN_CHUNK_BYTES = 16u << 20;        // two pinned staging buffers of this size
+constexpr int64_t INGEST_CHUNK_BYTES = 64ll << 20;   // rows landed / converted per step
+
+// dst (device) <- src (host), ordered on the handle's stream.  Page-locked sources go straight
+// to the copy engine; pageable ones through two pinned buffers filled by the CopyPool, so the
+// CPU copy of piece i+1 overlaps the DMA of piece i (the driver's own pageable path: ~11 GB/s).
+int ensure_pinned_staging(b2ip_handle h) {
+    if (h->pin[0]) return B2IP_OK;
+    for (int b = 0; b < 2; b++) {
+        CU_TRY(h, cudaHostAlloc(&h->pin[b], PIN_CHUNK_BYTES, cudaHostAllocDefault));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->pin_ev[b], cudaEventDisableTiming));
+    }
+    int nt = 4;
+    if (const char* s = getenv("B2IP_COPY_THREADS")) nt = std::max(0, std::min(32, atoi(s)));
+    h->pool = new CopyPool(nt);
+    return B2IP_OK;
+}
+
+int host_to_device(b2ip_handle h, void* dst, const void* src, size_t bytes) {
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (pinned || bytes < (256u << 10)) {
+        CU_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        return B2IP_OK;
+    }
+    RC_TRY(ensure_pinned_staging(h));
+    for (size_t off = 0; off < bytes; off += PIN_CHUNK_BYTES) {
+        const size_t len = std::min(PIN_CHUNK_BYTES, bytes - off);
+        const int b = h->pin_next;
+        h->pin_next ^= 1;
+        CU_TRY(h, cudaEventSynchronize(h->pin_ev[b]));      // the DMA that last read this buffer is done
+        h->pool->copy(h->pin[b], static_cast<const char*>(src) + off, len);
+        CU_TRY(h, cudaMemcpyAsync(static_cast<char*>(dst) + off, h->pin[b], len, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaEventRecord(h->pin_ev[b], h->stream));
+    }
+    return B2IP_OK;
+}
+
+int ensure_pinned_staging(b2ip_handle h);
+
+// dst (host) <- src (device); complete on return.  Pageable destinations are filled from the
+// two pinned buffers, the CPU copy of piece i overlapping the DMA of piece i+1.
+int device_to_host(b2ip_handle h, void* dst, const void* src, size_t bytes) {
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (pinned || bytes < (256u << 10)) {
+        CU_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        return B2IP_OK;
+    }
+    RC_TRY(ensure_pinned_staging(h));
+    CU_TRY(h, cudaEventSynchronize(h->pin_ev[0]));
+    CU_TRY(h, cudaEventSynchronize(h->pin_ev[1]));
+    size_t prev_off = 0, prev_len = 0;
+    int prev_b = -1;
+    for (size_t off = 0; off < bytes; off += PIN_CHUNK_BYTES) {
+        const size_t len = std::min(PIN_CHUNK_BYTES, bytes - off);
+        const int b = h->pin_next;
+        h->pin_next ^= 1;
+        CU_TRY(h, cudaMemcpyAsync(h->pin[b], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaEventRecord(h->pin_ev[b], h->stream));
+        if (prev_b >= 0) {
+            CU_TRY(h, cudaEventSynchronize(h->pin_ev[prev_b]));
+            h->pool->copy(static_cast<char*>(dst) + prev_off, h->pin[prev_b], prev_len);
+        }
+        prev_b = b; prev_off = off; prev_len = len;
+    }
+    if (prev_b >= 0) {
+        CU_TRY(h, cudaEventSynchronize(h->pin_ev[prev_b]));
+        h->pool->copy(static_cast<char*>(dst) + prev_off, h->pin[prev_b], prev_len);
+    }
+    return B2IP_OK;
+}
+
 struct Guard {   // selects the index's device for the duration of a call
     int prev = -1;
     explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -228,11 +363,7 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
     CU_TRY(h, cudaMemcpyAsync(qlist_dev, qlist_host, static_cast<size_t>(nql) * sizeof(int),
                               cudaMemcpyHostToDevice, h->stream));
     const size_t sq_bytes = static_cast<size_t>(EXACT_QB) * h->d * sizeof(float);
-    CU_TRY(h, cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(sq_bytes)));
     const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
-    CU_TRY(h, cudaFuncSetAttribute(finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(fin_smem)));
     const int sgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
     const int hgrid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(h->sm_count) * 4));
     for (int64_t g0 = 0; g0 < nql; g0 += EXACT_QB) {
@@ -284,18 +415,16 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
     RC_TRY(ensure(h, h->flags, qb * sizeof(int)));
     RC_TRY(ensure(h, h->cand, static_cast<size_t>(qb) * cap * 8));
 
-    CU_TRY(h, cudaFuncSetAttribute(coarse_filter_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES));
-    CU_TRY(h, cudaFuncSetAttribute(coarse_filter_pair_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
-    CUtensorMap tmap_x_pair;
-    RC_TRY(make_tmap_bf16(h, &tmap_x_pair, h->x16, n, h->d_pad, 128));
     const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
-    CU_TRY(h, cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(fin_smem)));
-
-    CUtensorMap tmap_x;
-    RC_TRY(make_tmap_bf16(h, &tmap_x, h->x16, n, h->d_pad, TILE_X));
+    // tensor maps of the corpus are rebuilt only when the rows moved or grew
+    if (h->tmap_x_base != h->x16 || h->tmap_x_rows != n) {
+        RC_TRY(make_tmap_bf16(h, &h->tmap_x_pair, h->x16, n, h->d_pad, 128));
+        RC_TRY(make_tmap_bf16(h, &h->tmap_x, h->x16, n, h->d_pad, TILE_X));
+        h->tmap_x_base = h->x16;
+        h->tmap_x_rows = n;
+    }
+    const CUtensorMap& tmap_x_pair = h->tmap_x_pair;
+    const CUtensorMap& tmap_x = h->tmap_x;
 
     size_t ev_used = 0;
     std::vector<int> fallback;
@@ -303,16 +432,13 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         const int nqb = static_cast<int>(std::min<int64_t>(qb, nq - q0));
         h->stats.query_batches++;
         const float* qptr = q32 + q0 * h->d;
-        CU_TRY(h, cudaMemsetAsync(h->gstats, 0, GS_COUNT * sizeof(long long), h->stream));
-        prep_queries_kernel<<<(nqb + 7) / 8, 256, 0, h->stream>>>(
+        const int nq_pad = static_cast<int>(pad_q(nqb));
+        prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, h->stream>>>(
             qptr, reinterpret_cast<__nv_bfloat16*>(h->q16.p), nqb, h->d, h->d_pad, h->norm_stats,
             reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
             reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p),
-            reinterpret_cast<int*>(h->flags.p), h->sh);
+            reinterpret_cast<int*>(h->flags.p), h->sh, nq_pad, h->gstats);
         h->stats.total_launches++;
-        if (pad_q(nqb) > nqb)
-            CU_TRY(h, cudaMemsetAsync(static_cast<char*>(h->q16.p) + static_cast<size_t>(nqb) * h->d_pad * 2, 0,
-                                      static_cast<size_t>(pad_q(nqb) - nqb) * h->d_pad * 2, h->stream));
         CUtensorMap tmap_q;
         RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, TILE_Q));
         const bool use_pair = h->pair && nqb > TILE_Q && h->sm_count >= 2;
@@ -430,14 +556,15 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         if (q0 + qb >= nq) CU_TRY(h, cudaEventRecord(h->ev_t1, h->stream));
         CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
                                   cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        CU_TRY(h, cudaGetLastError());
         std::vector<int> hflags;
-        if (overflowed > 0 || fixed_schedule) {
+        if (h->h_gstats[GS_OVERFLOW] > 0) {       // rare: which queries go to the exact path
             hflags.resize(nqb);
             CU_TRY(h, cudaMemcpyAsync(hflags.data(), h->flags.p, nqb * sizeof(int),
                                       cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
         }
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
-        CU_TRY(h, cudaGetLastError());
         h->stats.rescored += h->h_gstats[GS_RESCORED];
         if (fixed_schedule) h->stats.candidates += h->h_gstats[GS_CANDIDATES];
         for (int i = 0; i < static_cast<int>(hflags.size()); i++)
@@ -532,8 +659,8 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     *out = nullptr;
     if (store_dtype != B2IP_STORE_F32 && store_dtype != B2IP_STORE_BF16 && store_dtype != B2IP_STORE_F16)
         return fail(nullptr, B2IP_ERR_INVALID, "store_dtype=%d: use B2IP_STORE_F32, B2IP_STORE_F16 or B2IP_STORE_BF16", store_dtype);
-    if (d <= 0 || d % 4 != 0 || d > 4096)
-        return fail(nullptr, B2IP_ERR_INVALID, "d=%d: dimension must be a multiple of 4 in [4,4096]", d);
+    if (d <= 0 || d % 4 != 0 || d > B2IP_MAX_D)
+        return fail(nullptr, B2IP_ERR_INVALID, "d=%d: dimension must be a multiple of 4 in [4,%d]", d, B2IP_MAX_D);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -581,6 +708,18 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
         qres != cudaDriverEntryPointSuccess || !fn)
         return bail(B2IP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    {   // opt-in shared memory sizes, once per process and device
+        // (upper bounds for the largest supported d, so handles of different d can coexist)
+        const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(B2IP_MAX_D) * sizeof(float);
+        if (cudaFuncSetAttribute(coarse_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(coarse_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(coarse_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(static_cast<size_t>(EXACT_QB) * B2IP_MAX_D * sizeof(float))) != cudaSuccess)
+            return bail(B2IP_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    }
     h->gx = std::max(1, h->sm_count / 2);   // = clusters of the pair kernel: one query tile per wave,
                                             // the corpus tiles of a group stay L2 resident (measured best)
     if (const char* s = getenv("B2IP_GX")) h->gx = std::max(1, atoi(s));
@@ -602,6 +741,11 @@ void b2ip_destroy(b2ip_handle h) {
     if (h->norm_stats) cudaFree(h->norm_stats);
     if (h->gstats) cudaFree(h->gstats);
     if (h->h_gstats) cudaFreeHost(h->h_gstats);
+    delete h->pool;
+    for (int b = 0; b < 2; b++) {
+        if (h->pin[b]) cudaFreeHost(h->pin[b]);
+        if (h->pin_ev[b]) cudaEventDestroy(h->pin_ev[b]);
+    }
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_fin) cudaEventDestroy(e);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -659,54 +803,55 @@ int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem)
     if (h->n + n >= (1ll << 31) - 512) return fail(h, B2IP_ERR_UNSUPPORTED, "a shard holds at most 2^31-512 rows (TMA coordinates are int32)");
     Guard g(h->device);
     RC_TRY(grow_rows(h, h->n + n));
-    const cudaMemcpyKind kind = mem == B2IP_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-    const int rgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 16));
-    // 16-bit storage ingests in bounded chunks through a staging buffer (there is no fp32 master)
-    const int64_t chunk = h->store16 ? std::min<int64_t>(n, 1 << 18) : n;
+    const bool host = mem == B2IP_MEM_HOST;
+    const size_t elem = src_dtype == B2IP_F32 ? 4 : 2;
+    const size_t row_bytes = static_cast<size_t>(h->d) * elem;
+    // Rows are processed in chunks: each chunk is landed on the device (host rows go through
+    // the double-buffered pinned staging of host_to_device, so the CPU-side copy of chunk i+1
+    // overlaps the DMA and the conversion kernels of chunk i), converted, and shadowed.
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, INGEST_CHUNK_BYTES / static_cast<int64_t>(row_bytes)));
+    const bool lands_in_master = host && src_dtype == B2IP_F32 && !h->store16;
+    const bool need_f32_stage = h->store16 && !same16 && !(src_dtype == B2IP_F32 && !host);
+    const size_t land_bytes = (host && !lands_in_master) ? static_cast<size_t>(chunk) * row_bytes : 0;
+    const size_t land_pad = (land_bytes + 255) & ~static_cast<size_t>(255);
+    if (land_bytes || need_f32_stage)
+        RC_TRY(ensure(h, h->stage, land_pad + (need_f32_stage ? static_cast<size_t>(chunk) * h->d * sizeof(float) : 0)));
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t cn = std::min<int64_t>(chunk, n - c0);
         const size_t count = static_cast<size_t>(cn) * h->d;
         const int64_t r0 = h->n + c0;
+        const int rgrid = static_cast<int>(std::min<int64_t>((cn + 7) / 8, static_cast<int64_t>(h->sm_count) * 16));
+        const char* src_any = static_cast<const char*>(rows) + static_cast<size_t>(c0) * row_bytes;
+        float* master = h->store16 ? nullptr : h->x32 + r0 * h->d;
+        const void* src_dev = src_any;                       // this chunk's source rows, on the device
+        if (host) {
+            void* land = lands_in_master ? static_cast<void*>(master) : h->stage.p;
+            RC_TRY(host_to_device(h, land, src_any, count * elem));
+            src_dev = land;
+        }
         if (same16) {
-            const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(rows) + static_cast<size_t>(c0) * h->d;
-            if (mem == B2IP_MEM_HOST) {
-                RC_TRY(ensure(h, h->stage, count * 2));
-                CU_TRY(h, cudaMemcpyAsync(h->stage.p, src, count * 2, kind, h->stream));
-                src = static_cast<const __nv_bfloat16*>(h->stage.p);
-            }
-            ingest_16bit_rows_kernel<<<rgrid, 256, 0, h->stream>>>(src, h->x16, r0, r0 + cn, h->d, h->d_pad,
-                                                                   h->norm_stats, h->sh);
-            if (mem == B2IP_MEM_HOST) CU_TRY(h, cudaStreamSynchronize(h->stream));   // staging buffer is reused
+            ingest_16bit_rows_kernel<<<rgrid, 256, 0, h->stream>>>(
+                static_cast<const __nv_bfloat16*>(src_dev), h->x16, r0, r0 + cn, h->d, h->d_pad,
+                h->norm_stats, h->sh);
             continue;
         }
-        // fp32 destination of this chunk: the master rows, or a staging area (bf16 storage)
-        float* dst32;
-        size_t f16_off = 0;
-        if (h->store16) {
-            f16_off = count * sizeof(float);
-            RC_TRY(ensure(h, h->stage, f16_off + (src_dtype == B2IP_F16 && mem == B2IP_MEM_HOST ? count * 2 : 0)));
-            dst32 = static_cast<float*>(h->stage.p);
-        } else {
-            dst32 = h->x32 + r0 * h->d;
-            if (src_dtype == B2IP_F16 && mem == B2IP_MEM_HOST) RC_TRY(ensure(h, h->stage, count * 2));
-        }
+        // fp32 view of the chunk: the master rows, the caller's device buffer, or the staging area
+        const float* p32;
         if (src_dtype == B2IP_F32) {
-            const float* src = static_cast<const float*>(rows) + static_cast<size_t>(c0) * h->d;
-            if (h->store16 && mem == B2IP_MEM_DEVICE) dst32 = const_cast<float*>(src);   // convert in place from the caller's buffer
-            else CU_TRY(h, cudaMemcpyAsync(dst32, src, count * sizeof(float), kind, h->stream));
-        } else {
-            const __half* src = static_cast<const __half*>(rows) + static_cast<size_t>(c0) * h->d;
-            if (mem == B2IP_MEM_HOST) {
-                __half* st = reinterpret_cast<__half*>(static_cast<char*>(h->stage.p) + f16_off);
-                CU_TRY(h, cudaMemcpyAsync(st, src, count * 2, kind, h->stream));
-                src = st;
+            p32 = static_cast<const float*>(src_dev);
+            if (master && p32 != master) {
+                CU_TRY(h, cudaMemcpyAsync(master, p32, count * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+                p32 = master;
             }
+        } else {
+            float* dst32 = master ? master : reinterpret_cast<float*>(static_cast<char*>(h->stage.p) + land_pad);
             const int grid = static_cast<int>(std::min<size_t>((count / 2 + 255) / 256 + 1, 65535));
-            widen_f16_kernel<<<grid, 256, 0, h->stream>>>(src, dst32, static_cast<long long>(count));
+            widen_f16_kernel<<<grid, 256, 0, h->stream>>>(static_cast<const __half*>(src_dev), dst32,
+                                                         static_cast<long long>(count));
+            p32 = dst32;
         }
-        shadow_rows_kernel<<<rgrid, 256, 0, h->stream>>>(dst32, r0, h->x16, r0, r0 + cn, h->d, h->d_pad,
+        shadow_rows_kernel<<<rgrid, 256, 0, h->stream>>>(p32, r0, h->x16, r0, r0 + cn, h->d, h->d_pad,
                                                          h->norm_stats, !h->store16, h->sh);
-        if (h->store16) CU_TRY(h, cudaStreamSynchronize(h->stream));   // staging buffer is reused
     }
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -739,20 +884,34 @@ int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* o
     RC_TRY(ensure(h, h->qstage, static_cast<size_t>(nq) * h->d * sizeof(float)));
     RC_TRY(ensure(h, h->out_s, static_cast<size_t>(nq) * k * sizeof(float)));
     RC_TRY(ensure(h, h->out_r, static_cast<size_t>(nq) * k * sizeof(int64_t)));
-    CU_TRY(h, cudaMemcpyAsync(h->qstage.p, queries, static_cast<size_t>(nq) * h->d * sizeof(float),
-                              cudaMemcpyHostToDevice, h->stream));
+    RC_TRY(host_to_device(h, h->qstage.p, queries, static_cast<size_t>(nq) * h->d * sizeof(float)));
     RC_TRY(search_device(h, nq, static_cast<const float*>(h->qstage.p), k,
                          static_cast<float*>(h->out_s.p), static_cast<int64_t*>(h->out_r.p), mode));
-    CU_TRY(h, cudaMemcpyAsync(out_scores, h->out_s.p, static_cast<size_t>(nq) * k * sizeof(float),
-                              cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(out_rows, h->out_r.p, static_cast<size_t>(nq) * k * sizeof(int64_t),
-                              cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const size_t sb = static_cast<size_t>(nq) * k * sizeof(float), rb = static_cast<size_t>(nq) * k * sizeof(int64_t);
+    cudaPointerAttributes a1, a2;
+    const bool pin1 = cudaPointerGetAttributes(&a1, out_scores) == cudaSuccess && a1.type != cudaMemoryTypeUnregistered;
+    const bool pin2 = cudaPointerGetAttributes(&a2, out_rows) == cudaSuccess && a2.type != cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if ((pin1 && pin2) || sb + rb < (512u << 10)) {      // both on the copy engine, one synchronisation
+        CU_TRY(h, cudaMemcpyAsync(out_scores, h->out_s.p, sb, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(out_rows, h->out_r.p, rb, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        return B2IP_OK;
+    }
+    RC_TRY(device_to_host(h, out_scores, h->out_s.p, sb));
+    RC_TRY(device_to_host(h, out_rows, h->out_r.p, rb));
     return B2IP_OK;
 }
 
 int b2ip_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int n_lists,
                     const float* scores, const int64_t* rows, float* out_scores, int64_t* out_rows) {
+    return b2ip_merge_topk_strided(device, cuda_stream, nq, k, n_lists, scores, rows, nq * k, nq * k,
+                                   out_scores, out_rows);
+}
+
+int b2ip_merge_topk_strided(int device, void* cuda_stream, int64_t nq, int k, int n_lists,
+                            const float* scores, const int64_t* rows, int64_t scores_list_stride,
+                            int64_t rows_list_stride, float* out_scores, int64_t* out_rows) {
     if (nq < 0 || k < 1 || k > B2IP_MAX_K || n_lists < 1 || n_lists > 64)
         return fail(nullptr, B2IP_ERR_INVALID, "b2ip_merge_topk: nq=%lld k=%d n_lists=%d", (long long)nq, k, n_lists);
     if (nq == 0) return B2IP_OK;
@@ -766,8 +925,8 @@ int b2ip_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int n_list
     cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess) {
         merge_topk_kernel<<<static_cast<unsigned int>(nq), SEL_THREADS, smem, st>>>(
-            nq, k, n_lists, scores, reinterpret_cast<const long long*>(rows), out_scores,
-            reinterpret_cast<long long*>(out_rows), P);
+            nq, k, n_lists, scores, reinterpret_cast<const long long*>(rows), scores_list_stride,
+            rows_list_stride, out_scores, reinterpret_cast<long long*>(out_rows), P);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -792,8 +951,9 @@ int b2ip_export_rows(b2ip_handle h, int64_t row0, int64_t n, float* out, int mem
         if (mem == B2IP_MEM_DEVICE) { CU_TRY(h, cudaStreamSynchronize(h->stream)); return B2IP_OK; }
         src = tmp;
     }
+    if (mem == B2IP_MEM_HOST) return device_to_host(h, out, src, static_cast<size_t>(n) * h->d * sizeof(float));
     CU_TRY(h, cudaMemcpyAsync(out, src, static_cast<size_t>(n) * h->d * sizeof(float),
-                              mem == B2IP_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+                              cudaMemcpyDeviceToDevice, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return B2IP_OK;
 }
@@ -818,18 +978,14 @@ int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev
     RC_TRY(ensure(h, h->cnt, nq * sizeof(int)));
     RC_TRY(ensure(h, h->kept, nq * sizeof(int)));
     RC_TRY(ensure(h, h->flags, nq * sizeof(int)));
-    prep_queries_kernel<<<static_cast<int>((nq + 7) / 8), 256, 0, h->stream>>>(
+    prep_queries_kernel<<<static_cast<int>((pad_q(nq) + 7) / 8), 256, 0, h->stream>>>(
         queries_dev, reinterpret_cast<__nv_bfloat16*>(h->q16.p), static_cast<int>(nq), h->d, h->d_pad,
         h->norm_stats, reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
-        reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p), reinterpret_cast<int*>(h->flags.p), h->sh);
-    if (pad_q(nq) > nq)
-        CU_TRY(h, cudaMemsetAsync(static_cast<char*>(h->q16.p) + static_cast<size_t>(nq) * h->d_pad * 2, 0,
-                                  static_cast<size_t>(pad_q(nq) - nq) * h->d_pad * 2, h->stream));
+        reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p), reinterpret_cast<int*>(h->flags.p), h->sh,
+        static_cast<int>(pad_q(nq)), nullptr);
     CUtensorMap tmap_q, tmap_x;
     RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nq), h->d_pad, TILE_Q));
     RC_TRY(make_tmap_bf16(h, &tmap_x, h->x16, h->n, h->d_pad, TILE_X));
-    CU_TRY(h, cudaFuncSetAttribute(coarse_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   COARSE_SMEM_BYTES));
     CoarseParams cp{};
     cp.num_k_blocks = h->d_pad / KBLOCK_ELEMS;
     cp.q_tiles = static_cast<int>((nq + TILE_Q - 1) / TILE_Q);

@@ -178,10 +178,19 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
                                     const unsigned int* __restrict__ norm_stats,
                                     float* __restrict__ eps2, float* __restrict__ thr,
                                     int* __restrict__ cnt, int* __restrict__ kept,
-                                    int* __restrict__ flags, int sh) {
+                                    int* __restrict__ flags, int sh, int nq_pad,
+                                    long long* __restrict__ gstats) {
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (q >= nq) return;
+    if (blockIdx.x == 0 && threadIdx.x < GS_COUNT && gstats) gstats[threadIdx.x] = 0;
+    if (q >= nq) {
+        // rows that pad the last (pair) tile: zeros, so no TMA box hangs over the tensor's end
+        if (q < nq_pad) {
+            uint2* dst = reinterpret_cast<uint2*>(q16 + static_cast<long long>(q) * d_pad);
+            for (int j = lane; j < d_pad / 4; j += 32) dst[j] = make_uint2(0u, 0u);
+        }
+        return;
+    }
     const float4* src = reinterpret_cast<const float4*>(q32 + static_cast<long long>(q) * d);
     uint2* dst = reinterpret_cast<uint2*>(q16 + static_cast<long long>(q) * d_pad);
     float nh = 0.f, nd = 0.f;
@@ -681,7 +690,8 @@ __global__ void fill_padding_kernel(float* scores, long long* rows, long long co
 // (score desc, global row asc) and the first k written out.  smem: P u64 keys.
 __global__ void __launch_bounds__(SEL_THREADS)
 merge_topk_kernel(long long nq, int k, int n_lists, const float* __restrict__ scores,
-                  const long long* __restrict__ rows, float* __restrict__ out_scores,
+                  const long long* __restrict__ rows, long long scores_list_stride,
+                  long long rows_list_stride, float* __restrict__ out_scores,
                   long long* __restrict__ out_rows, int P) {
     extern __shared__ __align__(16) uint8_t msm[];
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(msm);
@@ -691,9 +701,9 @@ merge_topk_kernel(long long nq, int k, int n_lists, const float* __restrict__ sc
         unsigned long long key = 0ull;
         if (i < total) {
             const int l = i / k, j = i - l * k;
-            const long long src = (static_cast<long long>(l) * nq + q) * k + j;
-            const long long r = rows[src];
-            if (r >= 0) key = make_key(scores[src], static_cast<uint32_t>(r));
+            const long long src = q * k + j;
+            const long long r = rows[l * rows_list_stride + src];
+            if (r >= 0) key = make_key(scores[l * scores_list_stride + src], static_cast<uint32_t>(r));
         }
         sbuf[i] = key;
     }

@@ -60,6 +60,7 @@ enum {
 };
 
 #define B2IP_MAX_K 2048
+#define B2IP_MAX_D 4096
 
 /* Counters of the most recent b2ip_search on a handle (timings from CUDA events on the
  * handle's stream). */
@@ -132,6 +133,13 @@ int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* o
 int b2ip_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int n_lists,
                     const float* scores, const int64_t* rows, float* out_scores,
                     int64_t* out_rows);
+
+/* Same, for lists that are not back to back: list l's scores start at scores +
+ * l*scores_list_stride (floats), its rows at rows + l*rows_list_stride (int64s).  Lets every
+ * rank all-gather ONE packed buffer per search ([rows | scores] per rank) and merge in place. */
+int b2ip_merge_topk_strided(int device, void* cuda_stream, int64_t nq, int k, int n_lists,
+                            const float* scores, const int64_t* rows, int64_t scores_list_stride,
+                            int64_t rows_list_stride, float* out_scores, int64_t* out_rows);
 
 /* replaces faiss.write_index's read of the stored vectors       -- src/index.py:53
  * Copies rows [row0, row0+n) as fp32 into out ([n,d]). */

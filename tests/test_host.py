@@ -221,3 +221,55 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("C3")
+
+
+class _RecordingIndex:
+    """Stands in for Indexer: records the index_data call sequence."""
+    def __init__(self):
+        self.calls = []
+
+    def index_data(self, ids, embeddings):
+        self.calls.append((list(ids), np.array(embeddings, copy=True)))
+
+
+@pytest.mark.parametrize("sizes,batch", [
+    ([1500, 700, 2300], 1000), ([1000, 1000], 1000), ([5], 1000), ([999, 1, 1000, 1], 1000),
+    ([300, 0, 300], 250), ([2500], 1000),
+])
+def test_streaming_ingest_makes_the_reference_drivers_calls(tmp_path, built, sizes, batch):
+    """b2ip.ingest.index_encoded_data hands index_data the same (ids, embeddings) batches, in
+    the same order, as the reference driver loop (passage_retrieval.py:65-91, restated in
+    tests/helpers.py) -- without its np.vstack re-copies."""
+    import pickle
+    from helpers import ingest_like_reference_driver, synth
+    from b2ip.ingest import index_encoded_data
+    files, shards, start = [], [], 0
+    for i, n in enumerate(sizes):
+        emb = synth(n, 16, 100 + i, normalize=False).astype(np.float16) if n else np.zeros((0, 16), np.float16)
+        ids = [str(start + j) for j in range(n)]
+        start += n
+        path = tmp_path / f"passages_{i:02d}"
+        with open(path, "wb") as f:
+            pickle.dump((ids, emb), f)
+        files.append(str(path))
+        shards.append((ids, emb))
+    want, got = _RecordingIndex(), _RecordingIndex()
+    ingest_like_reference_driver(want, [s for s in shards if len(s[0])], batch)
+    index_encoded_data(got, files, batch)
+    assert len(got.calls) == len(want.calls)
+    for (gi, ge), (wi, we) in zip(got.calls, want.calls):
+        assert gi == wi
+        assert ge.dtype == we.dtype and np.array_equal(ge, we)
+
+
+def test_prefetch_propagates_errors_and_order(built):
+    from b2ip.ingest import prefetch
+    assert list(prefetch(iter(range(50)), depth=2)) == list(range(50))
+
+    def bad():
+        yield 1
+        raise KeyError("boom")
+    it = prefetch(bad())
+    assert next(it) == 1
+    with pytest.raises(KeyError):
+        next(it)
