@@ -1,0 +1,124 @@
+"""Drop-in replacement for the reference's `src/index.py` (Indexer over faiss.IndexFlatIP).
+
+Same class, methods, prints and return types as reference src/index.py:15-73 (re-exported under
+the reference's module path by `czech-contriever_b200/src/index.py`, and installed over the
+reference's own `src.index` by `python -m b2ip.dropin <script>`);
+the faiss object is replaced by `b2ip.Engine` (libb2ip.so, B200 only).  Differences, all
+deliberate:
+  * `n_subquantizers > 0` (faiss.IndexPQ, src/index.py:18-19) raises: approximate search is
+    not on this path and there is no CPU fallback.
+  * `index_batch_size` is a hint: queries are independent, the engine batches them itself.
+  * the id mapping of src/index.py:44 (nq*k Python str() calls) is done once per id at
+    first use and then by one fancy-index -- same strings, same `[-1]` = last-id quirk
+    for the -1 padding the reference has when the index holds fewer than k rows.
+  * storage (`store=` / env B2IP_STORE, default "auto"): the reference widens whatever it is
+    given to float32 (src/index.py:27).  Its default pipeline hands in float16 shards
+    (generate_passage_embeddings.py:75-76); widening is exact, so "auto" keeps such rows as
+    fp16 in HBM (a third of the memory, identical results) and moves the whole index to fp32
+    master rows the first time a chunk arrives that is not float16.
+"""
+import os
+import pickle
+from typing import List, Tuple
+
+import numpy as np
+
+from .engine import Engine
+from .faiss_io import stream_flat_ip_rows, write_flat_ip
+
+
+class Indexer(object):
+
+    def __init__(self, vector_sz, n_subquantizers=0, n_bits=8, device=None, store=None):
+        if n_subquantizers > 0:
+            raise NotImplementedError(
+                "IndexPQ (n_subquantizers > 0) is approximate search; the B200 engine implements "
+                "exact IndexFlatIP only and has no CPU fallback")
+        if device is None:
+            device = int(os.environ.get("B2IP_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        if store is None:
+            store = os.environ.get("B2IP_STORE", "auto")
+        if store not in ("auto", "f32", "f16"):
+            raise ValueError("store must be 'auto', 'f32' or 'f16' (an explicit 'f16' rounds fp32 rows)")
+        self.vector_sz = vector_sz
+        self.device = device
+        self.store = store
+        self.index = Engine(vector_sz, device, store="f16" if store == "f16" else "f32")
+        self.index_id_to_db_id = []
+        self._str_ids = None
+
+    def _is_f16(self, embeddings):
+        dt = getattr(embeddings, "dtype", None)
+        return dt is not None and str(dt).endswith("float16") and not str(dt).endswith("bfloat16")
+
+    def _restore(self, store):
+        """Moves the rows held so far into an engine with another storage type (exact:
+        fp16 -> fp32 widening)."""
+        new = Engine(self.vector_sz, self.device, store=store)
+        n = self.index.ntotal
+        new.reserve(n)
+        for r0 in range(0, n, 1 << 18):
+            new.add(self.index.export_rows(r0, min(1 << 18, n - r0)))
+        self.index.close()
+        self.index = new
+
+    def index_data(self, ids, embeddings):
+        self._update_id_mapping(ids)
+        # reference: embeddings.astype('float32'); fp16 is widened on the GPU (exact)
+        if self.store == "auto":
+            if self._is_f16(embeddings):
+                if self.index.ntotal == 0 and self.index.store != "f16":
+                    self.index.close()
+                    self.index = Engine(self.vector_sz, self.device, store="f16")
+            elif self.index.store == "f16":
+                self._restore("f32")
+        self.index.add(embeddings)
+
+        print(f'Total data indexed {len(self.index_id_to_db_id)}')
+
+    def search_knn(self, query_vectors: np.array, top_docs: int, index_batch_size: int = 2048) -> List[Tuple[List[object], List[float]]]:
+        query_vectors = np.asarray(query_vectors).astype('float32')
+        if len(query_vectors) == 0:
+            return []
+        scores, indexes = self.index.search(query_vectors, top_docs)
+        # convert to external ids
+        if self._str_ids is None or len(self._str_ids) != len(self.index_id_to_db_id):
+            self._str_ids = np.array([str(i) for i in self.index_id_to_db_id], dtype=object)
+        if len(self._str_ids) == 0:
+            raise IndexError('list index out of range')   # what the reference's [-1] lookup raises
+        db_ids = self._str_ids[indexes].tolist()
+        return [(db_ids[i], scores[i]) for i in range(len(db_ids))]
+
+    def serialize(self, dir_path):
+        index_file = os.path.join(dir_path, 'index.faiss')
+        meta_file = os.path.join(dir_path, 'index_meta.faiss')
+        print(f'Serializing index to {index_file}, meta data to {meta_file}')
+
+        write_flat_ip(index_file, self.vector_sz, self.index.ntotal, self.index.export_rows)
+        with open(meta_file, mode='wb') as f:
+            pickle.dump(self.index_id_to_db_id, f)
+
+    def deserialize_from(self, dir_path):
+        index_file = os.path.join(dir_path, 'index.faiss')
+        meta_file = os.path.join(dir_path, 'index_meta.faiss')
+        print(f'Loading index from {index_file}, meta data from {meta_file}')
+
+        d, ntotal, blocks = stream_flat_ip_rows(index_file)
+        index = Engine(d, self.device, store="f16" if self.store == "f16" else "f32")
+        index.reserve(ntotal)
+        for block in blocks:
+            index.add(block)
+        self.index.close()
+        self.index = index
+        self.vector_sz = d
+        print('Loaded index of type %s and size %d', type(self.index), self.index.ntotal)
+
+        with open(meta_file, "rb") as reader:
+            self.index_id_to_db_id = pickle.load(reader)
+        self._str_ids = None
+        assert len(
+            self.index_id_to_db_id) == self.index.ntotal, 'Deserialized index_id_to_db_id should match faiss index size'
+
+    def _update_id_mapping(self, db_ids: List):
+        self.index_id_to_db_id.extend(db_ids)
+        self._str_ids = None

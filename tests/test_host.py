@@ -273,3 +273,39 @@ def test_prefetch_propagates_errors_and_order(built):
     assert next(it) == 1
     with pytest.raises(KeyError):
         next(it)
+
+
+def test_dropin_launcher_replaces_src_index_in_a_reference_style_checkout(tmp_path, built):
+    """`python -m b2ip.dropin script.py`: the script's own `src` package wins on sys.path (as in
+    the reference checkout), yet `src.index.Indexer` is the B200 Indexer and sibling modules of
+    the reference's package stay importable; the reference's faiss-importing index.py never runs."""
+    import subprocess
+    import sys
+    co = tmp_path / "checkout"
+    (co / "src").mkdir(parents=True)
+    (co / "src" / "__init__.py").write_text("")
+    (co / "src" / "index.py").write_text("import faiss_that_is_not_installed\n")
+    (co / "src" / "other.py").write_text("VALUE = 41\n")
+    (co / "driver.py").write_text(
+        "import sys\nimport src.index\nimport src.other\n"
+        "print(src.index.Indexer.__module__, src.other.VALUE + 1, sys.argv[1:])\n"
+        "try:\n    src.index.Indexer(768, 16, 8)\nexcept NotImplementedError:\n    print('pq rejected')\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "czech-contriever_b200"))
+    out = subprocess.run([sys.executable, "-m", "b2ip.dropin", str(co / "driver.py"), "--n_docs", "100"],
+                         capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "b2ip.indexer 42 ['--n_docs', '100']" in out.stdout and "pq rejected" in out.stdout
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/passage_retrieval.py"),
+                    reason="reference checkout not present (GPU box)")
+def test_dropin_launcher_runs_the_unmodified_reference_driver(built):
+    """The real passage_retrieval.py imports and parses its flags under the launcher although
+    faiss is not installed (its `import src.index` resolves to the drop-in)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "czech-contriever_b200"))
+    out = subprocess.run([sys.executable, "-m", "b2ip.dropin", "/root/reference/passage_retrieval.py", "--help"],
+                         capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert "--passages_embeddings" in out.stdout and "--n_docs" in out.stdout
