@@ -412,6 +412,11 @@ def main():
         cpu, _ = cpu_reference_qps(args, sample_host, qs, steps=1, warmup=1)
 
     launches = int(sum_over_ranks(agg["launches"]))
+    # order-independent digest of the last step's results: identical at every N (the sharded
+    # search returns the single-GPU answer bit for bit), so the scaling runs check each other
+    checksum = {"ids_sum": int(I_last.sum().item()),
+                "ids_weighted": int((I_last * torch.arange(1, k + 1, device=dev)).sum().item() % (1 << 61)),
+                "scores_sum_f64": float(D_last.double().sum().item())}
     if rank == 0:
         line = {
             "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -420,7 +425,7 @@ def main():
             "dtype": f"{args.store if args.store != 'f32' else (args.shadow or 'bf16')} coarse / f32 rescore",
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "result_checksum": checksum,
             "detail": {"ingest_s": t_ing, "rows_per_gpu": hi - lo,
                        "candidates_per_query_per_step": agg["candidates"] / max(1, args.steps) / nq,
                        "rescored_per_query_per_step": agg["rescored"] / max(1, args.steps) / nq,

@@ -36,6 +36,20 @@ def install(package: str = "src") -> types.ModuleType:
     return mod
 
 
+def install_beir() -> bool:
+    """eval_beir.py / train.py never reach `Indexer`: src/beir_utils.py:14 does
+    `from beir.retrieval.search.dense import DenseRetrievalExactSearch` and builds it at :167.
+    When beir is importable, that name is rebound to the B200 searcher (b2ip/beir_search.py)
+    before the script imports src.beir_utils.  Returns False when beir is not installed."""
+    try:
+        dense = importlib.import_module("beir.retrieval.search.dense")
+    except ImportError:
+        return False
+    from .beir_search import DenseRetrievalExactSearch
+    dense.DenseRetrievalExactSearch = DenseRetrievalExactSearch
+    return True
+
+
 def main(argv=None) -> None:
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
@@ -45,6 +59,7 @@ def main(argv=None) -> None:
     if script_dir not in sys.path:
         sys.path.insert(0, script_dir)              # what `python script.py` does
     install()
+    install_beir()
     sys.argv = [script] + argv[1:]
     runpy.run_path(script, run_name="__main__")
 

@@ -286,15 +286,22 @@ def test_dropin_launcher_replaces_src_index_in_a_reference_style_checkout(tmp_pa
     (co / "src" / "__init__.py").write_text("")
     (co / "src" / "index.py").write_text("import faiss_that_is_not_installed\n")
     (co / "src" / "other.py").write_text("VALUE = 41\n")
+    # a stand-in for the (absent) beir package, shaped like the import in src/beir_utils.py:14
+    dense = co / "beir" / "retrieval" / "search" / "dense"
+    dense.mkdir(parents=True)
+    for d in (co / "beir", co / "beir" / "retrieval", co / "beir" / "retrieval" / "search"):
+        (d / "__init__.py").write_text("")
+    (dense / "__init__.py").write_text("class DenseRetrievalExactSearch:\n    pass\n")
     (co / "driver.py").write_text(
         "import sys\nimport src.index\nimport src.other\n"
-        "print(src.index.Indexer.__module__, src.other.VALUE + 1, sys.argv[1:])\n"
+        "from beir.retrieval.search.dense import DenseRetrievalExactSearch as DRES\n"
+        "print(src.index.Indexer.__module__, src.other.VALUE + 1, sys.argv[1:], DRES.__module__)\n"
         "try:\n    src.index.Indexer(768, 16, 8)\nexcept NotImplementedError:\n    print('pq rejected')\n")
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "czech-contriever_b200"))
     out = subprocess.run([sys.executable, "-m", "b2ip.dropin", str(co / "driver.py"), "--n_docs", "100"],
                          capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=120)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "b2ip.indexer 42 ['--n_docs', '100']" in out.stdout and "pq rejected" in out.stdout
+    assert "b2ip.indexer 42 ['--n_docs', '100'] b2ip.beir_search" in out.stdout and "pq rejected" in out.stdout
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/passage_retrieval.py"),
