@@ -723,6 +723,8 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     h->gx = std::max(1, h->sm_count / 2);   // = clusters of the pair kernel: one query tile per wave,
                                             // the corpus tiles of a group stay L2 resident (measured best)
     if (const char* s = getenv("B2IP_GX")) h->gx = std::max(1, atoi(s));
+    if (const char* s = getenv("B2IP_HINT_Q")) h->hint_q = atoi(s);
+    if (const char* s = getenv("B2IP_HINT_X")) h->hint_x = atoi(s);
     if (const char* s = getenv("B2IP_CAND_BUDGET_MB")) h->cand_budget_bytes = std::max(1ll, atoll(s)) << 20;
     memset(&h->stats, 0, sizeof(h->stats));
     *out = h;
@@ -809,9 +811,11 @@ int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem)
     // Rows are processed in chunks: each chunk is landed on the device (host rows go through
     // the double-buffered pinned staging of host_to_device, so the CPU-side copy of chunk i+1
     // overlaps the DMA and the conversion kernels of chunk i), converted, and shadowed.
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, INGEST_CHUNK_BYTES / static_cast<int64_t>(row_bytes)));
     const bool lands_in_master = host && src_dtype == B2IP_F32 && !h->store16;
     const bool need_f32_stage = h->store16 && !same16 && !(src_dtype == B2IP_F32 && !host);
+    // device rows that need no staging area are converted in one piece
+    const int64_t chunk = (!host && !need_f32_stage)
+        ? n : std::max<int64_t>(1, std::min<int64_t>(n, INGEST_CHUNK_BYTES / static_cast<int64_t>(row_bytes)));
     const size_t land_bytes = (host && !lands_in_master) ? static_cast<size_t>(chunk) * row_bytes : 0;
     const size_t land_pad = (land_bytes + 255) & ~static_cast<size_t>(255);
     if (land_bytes || need_f32_stage)
