@@ -22,7 +22,7 @@ MAX_K = 2048
 SYMBOLS = (
     "b2ip_create", "b2ip_create_ex", "b2ip_destroy", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_ntotal",
     "b2ip_dim", "b2ip_set_row_offset", "b2ip_search", "b2ip_merge_topk", "b2ip_merge_topk_strided", "b2ip_export_rows",
-    "b2ip_stats", "b2ip_last_error", "b2ip_debug_coarse_scores", "b2ip_version",
+    "b2ip_copy_to_device", "b2ip_copy_to_host", "b2ip_stats", "b2ip_last_error", "b2ip_debug_coarse_scores", "b2ip_version",
 )
 
 
@@ -80,6 +80,8 @@ def load() -> ctypes.CDLL:
     lib.b2ip_merge_topk.argtypes = [i32, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.b2ip_merge_topk_strided.argtypes = [i32, vp, i64, i32, i32, vp, vp, i64, i64, vp, vp]
     lib.b2ip_export_rows.argtypes = [vp, i64, i64, vp, i32]
+    lib.b2ip_copy_to_device.argtypes = [vp, vp, vp, i64]
+    lib.b2ip_copy_to_host.argtypes = [vp, vp, vp, i64]
     lib.b2ip_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b2ip_last_error.argtypes = [vp]
     lib.b2ip_last_error.restype = ctypes.c_char_p
@@ -87,7 +89,8 @@ def load() -> ctypes.CDLL:
     lib.b2ip_version.restype = ctypes.c_char_p
     for name in ("b2ip_create", "b2ip_create_ex", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_dim",
                  "b2ip_set_row_offset", "b2ip_search", "b2ip_merge_topk", "b2ip_merge_topk_strided",
-                 "b2ip_export_rows", "b2ip_stats", "b2ip_debug_coarse_scores"):
+                 "b2ip_export_rows", "b2ip_stats", "b2ip_debug_coarse_scores", "b2ip_copy_to_device",
+                 "b2ip_copy_to_host"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib

@@ -146,6 +146,24 @@ class Engine:
                                     m, MEM_HOST), self._h)
         return D, I
 
+    def upload(self, dst, src: np.ndarray) -> None:
+        """dst (torch CUDA tensor on this engine's device) <- src (host array of the same byte
+        size), through the handle's pinned double-buffered staging."""
+        src = np.ascontiguousarray(src)
+        assert dst.is_cuda and dst.device.index == self.device and dst.is_contiguous()
+        assert dst.numel() * dst.element_size() == src.nbytes
+        check(self._lib.b2ip_copy_to_device(self._h, ctypes.c_void_p(dst.data_ptr()),
+                                            ctypes.c_void_p(src.ctypes.data), src.nbytes), self._h)
+
+    def download(self, src, dst: np.ndarray) -> None:
+        """dst (C-contiguous host array) <- src (torch CUDA tensor on this engine's device)."""
+        assert src.is_cuda and src.device.index == self.device and src.is_contiguous()
+        assert dst.flags["C_CONTIGUOUS"] and src.numel() * src.element_size() == dst.nbytes
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()
+        check(self._lib.b2ip_copy_to_host(self._h, ctypes.c_void_p(dst.ctypes.data),
+                                          ctypes.c_void_p(src.data_ptr()), dst.nbytes), self._h)
+
     def stats(self) -> dict:
         s = Stats()
         check(self._lib.b2ip_stats(self._h, ctypes.byref(s)), self._h)

@@ -16,6 +16,10 @@ deliberate:
     (generate_passage_embeddings.py:75-76); widening is exact, so "auto" keeps such rows as
     fp16 in HBM (a third of the memory, identical results) and moves the whole index to fp32
     master rows the first time a chunk arrives that is not float16.
+  * devices (`device=` / env B2IP_DEVICES): an int is one GPU (default: B2IP_DEVICE, else
+    LOCAL_RANK, else 0); "all" or a list row-shards the index over those GPUs from this single
+    process (`b2ip.multi.MultiGpuEngine`) -- the reference driver is single-process, so this
+    is how an unmodified passage_retrieval.py uses a whole 8-GPU box.
 """
 import os
 import pickle
@@ -24,6 +28,7 @@ from typing import List, Tuple
 import numpy as np
 
 from .engine import Engine
+from .multi import MultiGpuEngine
 from .faiss_io import stream_flat_ip_rows, write_flat_ip
 
 
@@ -34,6 +39,10 @@ class Indexer(object):
             raise NotImplementedError(
                 "IndexPQ (n_subquantizers > 0) is approximate search; the B200 engine implements "
                 "exact IndexFlatIP only and has no CPU fallback")
+        if device is None and os.environ.get("B2IP_DEVICES"):
+            device = os.environ["B2IP_DEVICES"]
+        if isinstance(device, str) and device != "all":
+            device = [int(x) for x in device.split(",") if x.strip() != ""]
         if device is None:
             device = int(os.environ.get("B2IP_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         if store is None:
@@ -43,9 +52,17 @@ class Indexer(object):
         self.vector_sz = vector_sz
         self.device = device
         self.store = store
-        self.index = Engine(vector_sz, device, store="f16" if store == "f16" else "f32")
+        self.index = self._new_engine(vector_sz, "f16" if store == "f16" else "f32")
         self.index_id_to_db_id = []
         self._str_ids = None
+
+    def _new_engine(self, d, store):
+        if self.device == "all":
+            return MultiGpuEngine(d, None, store=store)
+        if isinstance(self.device, (list, tuple)):
+            return MultiGpuEngine(d, self.device, store=store) if len(self.device) > 1 \
+                else Engine(d, self.device[0], store=store)
+        return Engine(d, self.device, store=store)
 
     def _is_f16(self, embeddings):
         dt = getattr(embeddings, "dtype", None)
@@ -54,7 +71,7 @@ class Indexer(object):
     def _restore(self, store):
         """Moves the rows held so far into an engine with another storage type (exact:
         fp16 -> fp32 widening)."""
-        new = Engine(self.vector_sz, self.device, store=store)
+        new = self._new_engine(self.vector_sz, store)
         n = self.index.ntotal
         new.reserve(n)
         for r0 in range(0, n, 1 << 18):
@@ -69,7 +86,7 @@ class Indexer(object):
             if self._is_f16(embeddings):
                 if self.index.ntotal == 0 and self.index.store != "f16":
                     self.index.close()
-                    self.index = Engine(self.vector_sz, self.device, store="f16")
+                    self.index = self._new_engine(self.vector_sz, "f16")
             elif self.index.store == "f16":
                 self._restore("f32")
         self.index.add(embeddings)
@@ -104,7 +121,7 @@ class Indexer(object):
         print(f'Loading index from {index_file}, meta data from {meta_file}')
 
         d, ntotal, blocks = stream_flat_ip_rows(index_file)
-        index = Engine(d, self.device, store="f16" if self.store == "f16" else "f32")
+        index = self._new_engine(d, "f16" if self.store == "f16" else "f32")
         index.reserve(ntotal)
         for block in blocks:
             index.add(block)

@@ -962,6 +962,24 @@ int b2ip_export_rows(b2ip_handle h, int64_t row0, int64_t n, float* out, int mem
     return B2IP_OK;
 }
 
+int b2ip_copy_to_device(b2ip_handle h, void* dst_device, const void* src_host, int64_t bytes) {
+    if (!h) return B2IP_ERR_INVALID;
+    if (bytes < 0 || (bytes > 0 && (!dst_device || !src_host))) return fail(h, B2IP_ERR_INVALID, "b2ip_copy_to_device: bad arguments");
+    if (bytes == 0) return B2IP_OK;
+    Guard g(h->device);
+    RC_TRY(host_to_device(h, dst_device, src_host, static_cast<size_t>(bytes)));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return B2IP_OK;
+}
+
+int b2ip_copy_to_host(b2ip_handle h, void* dst_host, const void* src_device, int64_t bytes) {
+    if (!h) return B2IP_ERR_INVALID;
+    if (bytes < 0 || (bytes > 0 && (!dst_host || !src_device))) return fail(h, B2IP_ERR_INVALID, "b2ip_copy_to_host: bad arguments");
+    if (bytes == 0) return B2IP_OK;
+    Guard g(h->device);
+    return device_to_host(h, dst_host, src_device, static_cast<size_t>(bytes));
+}
+
 int b2ip_stats(b2ip_handle h, b2ip_stats_t* out) {
     if (!h || !out) return B2IP_ERR_INVALID;
     *out = h->stats;

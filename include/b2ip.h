@@ -145,6 +145,15 @@ int b2ip_merge_topk_strided(int device, void* cuda_stream, int64_t nq, int k, in
  * Copies rows [row0, row0+n) as fp32 into out ([n,d]). */
 int b2ip_export_rows(b2ip_handle h, int64_t row0, int64_t n, float* out, int mem);
 
+/* Host <-> device copies through the handle's pinned double-buffered staging (a pool of copy
+ * threads fills / drains two page-locked buffers while the copy engine moves the other one):
+ * what b2ip_add / b2ip_search use for pageable host buffers, exposed for callers that keep
+ * queries or results in their own device buffers (the single-process multi-GPU Indexer uploads
+ * the queries once and fans them out over NVLink).  Synchronous; `*_device` pointers must be
+ * valid on the handle's device. */
+int b2ip_copy_to_device(b2ip_handle h, void* dst_device, const void* src_host, int64_t bytes);
+int b2ip_copy_to_host(b2ip_handle h, void* dst_host, const void* src_device, int64_t bytes);
+
 int b2ip_stats(b2ip_handle h, b2ip_stats_t* out);
 const char* b2ip_last_error(b2ip_handle h);
 

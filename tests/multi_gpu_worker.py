@@ -36,6 +36,19 @@ for k in (10, 100, 1000):
         idx2.add_replicated(x[a:a + 7000])
     D2, I2 = idx2.search(qd, k)
     assert torch.equal(I2, I) and torch.equal(D2, D), f"k={k}: replicated ingest differs"
+if rank == 0:
+    # the single-process driver of the same shards (b2ip.multi): one engine per visible GPU
+    from b2ip import MultiGpuEngine
+    m = MultiGpuEngine(d)
+    assert len(m.engines) >= world
+    m.add(x[:25_000]); m.add(x[25_000:])
+    whole = Engine(d, local)
+    whole.add(x)
+    for k in (10, 100):
+        Dw, Iw = whole.search(q, k)
+        Dm, Im = m.search(q, k)
+        assert np.array_equal(Im, Iw) and np.array_equal(Dm, Dw), f"k={k}: MultiGpuEngine differs"
+    m.close()
 dist.barrier()
 dist.destroy_process_group()
 print(f"rank {rank} ok", flush=True)

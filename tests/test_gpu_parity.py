@@ -431,6 +431,49 @@ def test_indexer_drop_in(fo, tmp_path):
         assert a == b and np.array_equal(sa, sb)
 
 
+def test_single_process_multi_engine_equals_one_engine(fo, tmp_path):
+    """b2ip.multi.MultiGpuEngine (here: three shards on the one visible GPU) returns exactly what a
+    single Engine returns -- ids, scores, ties -- for one-shot and chunked ingest, host and device
+    queries, and exports rows by global id."""
+    import torch
+    from b2ip import Engine, MultiGpuEngine
+    x = synth(30_000, 256, 111)
+    x[20_000:20_040] = x[5:45]                       # exact ties across shards
+    q = synth(90, 256, 112)
+    whole = Engine(256, 0)
+    whole.add(x)
+    for chunks in ([(0, 30_000)], [(0, 7000), (7000, 7001), (7001, 19_000), (19_000, 30_000)]):
+        m = MultiGpuEngine(256, [0, 0, 0])
+        for a, b in chunks:
+            m.add(x[a:b])
+        assert m.ntotal == 30_000
+        for k in (1, 10, 100):
+            Dw, Iw = whole.search(q, k)
+            D, I = m.search(q, k)
+            assert np.array_equal(I, Iw) and np.array_equal(D, Dw)
+            Dt, It = m.search(torch.from_numpy(q).cuda(), k)
+            assert np.array_equal(It.cpu().numpy(), Iw) and np.array_equal(Dt.cpu().numpy(), Dw)
+        np.testing.assert_array_equal(m.export_rows(6990, 3000), x[6990:9990])
+        assert m.stats()["coarse_launches"] >= 3
+        m.close()
+    # through the drop-in Indexer: device list -> sharded engine, same search_knn output
+    from src.index import Indexer
+    ids = [f"doc{i}" for i in range(30_000)]
+    one, many = Indexer(256, 0, 8, device=0), Indexer(256, 0, 8, device=[0, 0])
+    for idx in (one, many):
+        idx.index_data(ids[:12_345], x[:12_345])
+        idx.index_data(ids[12_345:], x[12_345:])
+    ra, rb = one.search_knn(q, 20), many.search_knn(q, 20)
+    for (ia, sa), (ib, sb) in zip(ra, rb):
+        assert ia == ib and np.array_equal(sa, sb)
+    many.serialize(str(tmp_path))
+    again = Indexer(256, 0, 8, device=[0, 0])
+    again.deserialize_from(str(tmp_path))
+    rc = again.search_knn(q, 20)
+    for (ia, sa), (ic, sc) in zip(ra, rc):
+        assert ia == ic and np.array_equal(sa, sc)
+
+
 def test_indexer_rejects_pq():
     from src.index import Indexer
     with pytest.raises(NotImplementedError):

@@ -316,3 +316,24 @@ def test_dropin_launcher_runs_the_unmodified_reference_driver(built):
                          capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
     assert "--passages_embeddings" in out.stdout and "--n_docs" in out.stdout
+
+
+def test_segment_map_local_to_global(built):
+    """Row bookkeeping of the single-process multi-GPU engine (b2ip/multi.py)."""
+    import torch
+    from b2ip.multi import SegmentMap
+    m = SegmentMap()
+    m.append(100, 50)            # local 0..49   -> global 100..149
+    assert m.single_offset() == 100
+    m.append(150, 10)            # contiguous: merged into the same segment
+    assert m.segments == [(0, 100, 60)] and m.single_offset() == 100
+    m.append(400, 20)            # local 60..79  -> global 400..419
+    m.append(1000, 5)            # local 80..84  -> global 1000..1004
+    assert m.single_offset() is None and m.n_local == 85
+    loc = torch.tensor([[0, 59, 60, 79], [80, 84, -1, -1]])
+    assert m.to_global(loc).tolist() == [[100, 159, 400, 419], [1000, 1004, -1, -1]]
+    assert list(m.overlaps(0, 100)) == []
+    assert list(m.overlaps(120, 405)) == [(20, 120, 40), (60, 400, 5)]
+    assert list(m.overlaps(419, 2000)) == [(79, 419, 1), (80, 1000, 5)]
+    with pytest.raises(ValueError):
+        m.append(900, 1)
