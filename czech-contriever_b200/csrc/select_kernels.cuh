@@ -45,7 +45,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 enum { SH_BF16 = 0, SH_F16 = 1 };
 
 __device__ __forceinline__ float sat_f16(float v) {
-    return (v != v) ? v : fminf(fmaxf(v, -65504.f), 65504.f);      // NaN stays NaN
+    // finite values saturate; NaN and +-inf pass through unchanged (a row that scores inf in
+    // fp32 must score inf in the coarse pass too)
+    return (fabsf(v) <= FLT_MAX) ? fminf(fmaxf(v, -65504.f), 65504.f) : v;
+}
+__device__ __forceinline__ bool finite4(float4 v) {
+    return fabsf(v.x) <= FLT_MAX && fabsf(v.y) <= FLT_MAX && fabsf(v.z) <= FLT_MAX && fabsf(v.w) <= FLT_MAX;
 }
 __device__ __forceinline__ uint32_t pack2_sh(float a, float b, int sh) {
     if (sh == SH_F16) {
@@ -91,9 +96,11 @@ __global__ void shadow_rows_kernel(const float* __restrict__ src, long long src_
         const float4* srow = reinterpret_cast<const float4*>(src + (r - src_row0) * d);
         uint2* dst = reinterpret_cast<uint2*>(x16 + r * d_pad);
         float nx = 0.f, nd = 0.f;
+        bool ok = true;
         for (int j = lane; j < d_pad / 4; j += 32) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < d / 4) v = __ldg(srow + j);
+            ok = ok && finite4(v);
             uint2 o;
             o.x = pack2_sh(v.x, v.y, sh);
             o.y = pack2_sh(v.z, v.w, sh);
@@ -106,8 +113,14 @@ __global__ void shadow_rows_kernel(const float* __restrict__ src, long long src_
         }
         nx = warp_sum(nx);
         nd = warp_sum(nd);
-        if (nx == nx) mx = fmaxf(mx, nx);   // NaN rows never score, keep them out of the bound
-        if (nd == nd && count_delta) md = fmaxf(md, nd);
+        // Rows with a NaN / inf ELEMENT stay out of the bound: their coarse score is NaN / +-inf
+        // exactly when their fp32 score is, so they need no error margin (NaN never reports,
+        // +inf always does and is rescored).  A finite row whose norm overflows stays in: the
+        // bound becomes inf and the affected queries take the exact path.
+        if (__all_sync(0xffffffffu, ok)) {
+            mx = fmaxf(mx, nx);
+            if (count_delta) md = fmaxf(md, nd);
+        }
     }
     if (lane == 0) {
         // non-negative floats order like their bit patterns
@@ -130,15 +143,17 @@ __global__ void ingest_16bit_rows_kernel(const __nv_bfloat16* __restrict__ src,
         const uint32_t* srow = reinterpret_cast<const uint32_t*>(src + (r - row0) * d);
         uint32_t* dst = reinterpret_cast<uint32_t*>(x16 + r * d_pad);
         float nx = 0.f;
+        bool ok = true;
         for (int j = lane; j < d_pad / 2; j += 32) {
             uint32_t v = 0u;
             if (j < d / 2) v = srow[j];
             const float2 f = unpack2_sh(v, sh);
+            ok = ok && fabsf(f.x) <= FLT_MAX && fabsf(f.y) <= FLT_MAX;
             nx += f.x * f.x + f.y * f.y;
             dst[j] = v;
         }
         nx = warp_sum(nx);
-        if (nx == nx) mx = fmaxf(mx, nx);
+        if (__all_sync(0xffffffffu, ok)) mx = fmaxf(mx, nx);
     }
     if (lane == 0) atomicMax(norm_stats + 0, __float_as_uint(mx));
 }
@@ -215,6 +230,9 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
         const float acc = static_cast<float>(d_pad) * 1.1920929e-7f;   // d_pad * 2^-23
         float e = qh * dx + dq * nx + acc * qh * (nx + dx);
         e = e * 1.001f + FLT_MIN;          // norms above were themselves rounded
+        // no usable bound (overflowing norms, inf in the query): admit everything; the query
+        // then overflows its list and is answered by the exact path
+        if (!(e <= FLT_MAX)) e = INFINITY;
         eps2[q] = 2.f * e;
         thr[q] = -INFINITY;
         cnt[q] = 0;
@@ -412,6 +430,7 @@ refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
     const unsigned long long pk = block_radix_select(src, n, k, 4, hist, &s_prefix, &s_krem);
     const float ck = unorder_f32(static_cast<uint32_t>(pk >> 32));
     float t = __fsub_rd(ck, eps2[q]);
+    if (!(t == t)) t = -INFINITY;                    // inf - inf: no usable threshold
     t = nextafterf(t, -INFINITY);                    // admission test is strict
     const int m = (src == keys) ? block_compact(src, n, false, order_f32(t), 0ull, keys, s_warp)
                                 : block_compact_disjoint(src, n, false, order_f32(t), 0ull, keys, s_warp);

@@ -510,3 +510,51 @@ def test_c2_scale_subset(fo):
     xh, qh = x.cpu().numpy(), q[torch.from_numpy(sel).cuda()].cpu().numpy()
     Do, Io = fo.search(qh, xh, k)
     fo.compare_topk(D[sel], I[sel], Do, Io, qh, xh, rtol=RTOL)
+
+
+@pytest.mark.parametrize("store,shadow", [("f32", "bf16"), ("f32", "f16"), ("f16", None)])
+def test_non_finite_values_follow_faiss(fo, store, shadow):
+    """NaN / inf in the corpus or in a query (fp16 encoders do overflow): faiss never returns a
+    NaN score, returns +inf scores first, and pads a query that scores NaN everywhere.  A row
+    with a non-finite element must not poison the error bound of the other rows."""
+    from b2ip import Engine
+    n, d, k = 20_000, 256, 20
+    x = synth(n, d, 131)
+    x[11] = np.nan                    # never reported
+    x[500, 3] = np.inf                # +inf or -inf score depending on the query's sign there
+    x[9000, 7] = -np.inf
+    x[15000, 1] = np.inf; x[15000, 2] = -np.inf     # +inf, -inf or NaN (inf - inf) by the query's signs
+    q = synth(24, d, 132)
+    q[5] = np.nan                     # scores NaN everywhere -> all padding
+    if store == "f16":
+        x = x.astype(np.float16).astype(np.float32)
+    e = Engine(d, 0, store=store, shadow=shadow)
+    e.add(x)
+    for mode in ("tensor", "exact"):
+        D, I = e.search(q, k, mode=mode)
+        Do, Io = fo.search(q, x, k)
+        assert not np.isnan(D).any()
+        assert (I[5] == -1).all() and (D[5] == np.finfo(np.float32).min).all()
+        assert np.array_equal(I[5], Io[5])
+        assert not np.isin(I, [11]).any()
+        assert np.array_equal(np.isposinf(D), np.isposinf(Do))
+        rows = [i for i in range(24) if i != 5]
+        # rows that score +inf come first, the rest as usual
+        for r in rows:                            # (order among equal scores is heap-defined in faiss)
+            assert sorted(I[r][np.isposinf(D[r])]) == sorted(Io[r][np.isposinf(Do[r])])
+        fin = np.isfinite(Do[rows]).all(axis=1)
+        sel = [r for r, f in zip(rows, fin) if f]
+        xs = x.copy()
+        xs[[11, 500, 9000, 15000]] = 0.0          # tie classification only needs finite rows
+        Dm, Im, Dom, Iom = D[rows].copy(), I[rows].copy(), Do[rows].copy(), Io[rows].copy()
+        inf_mask = np.isposinf(Dom)
+        Dm[inf_mask] = 0; Dom[inf_mask] = 0       # compared above
+        fo.compare_topk(Dm, Im, Dom, Iom, q[rows], xs, rtol=RTOL)
+    if store == "f32":
+        assert e.stats()["mode_used"] == 2
+    e2 = Engine(d, 0, store=store, shadow=shadow)
+    e2.add(x)
+    e2.search(q, k, mode="tensor")
+    st = e2.stats()
+    # the non-finite rows did not push everything onto the exact path
+    assert st["fallback_queries"] <= 1, st
