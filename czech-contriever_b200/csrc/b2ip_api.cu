@@ -83,8 +83,12 @@ struct b2ip_index_s {
     int dbg = 0;
     int verbose = 0;
     int pair = 1;                         // CTA-pair (cta_group::2) scoring kernel when nq > 128
+    int dense_first = 1;                  // first slab stored positionally (no counters / hit extraction)
+    int fuse_refresh = 1;                 // last threshold refresh inside the finalize kernel
     long long cand_budget_bytes = 6ll << 30;
     CUtensorMap tmap_x, tmap_x_pair;      // cached TMA descriptors of x16 (single / pair box)
+    size_t timing_events = 0;             // event triples of the last tensor search (read by b2ip_stats)
+    bool timing_pending = false;
     const void* tmap_x_base = nullptr;
     int64_t tmap_x_rows = -1;
 };
@@ -433,11 +437,18 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         h->stats.query_batches++;
         const float* qptr = q32 + q0 * h->d;
         const int nq_pad = static_cast<int>(pad_q(nqb));
+        // first slab: every row is a candidate (no threshold yet) and is stored at its own
+        // position in the list, so the fill counters start at the slab size
+        int64_t slab = std::min<int64_t>(cap, std::max<int64_t>(1024, 8ll * k));
+        slab = slab / TILE_X * TILE_X;
+        const int64_t first_slab = std::min<int64_t>(slab, n);
+        const bool dense_first = h->dense_first != 0;
         prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, h->stream>>>(
             qptr, reinterpret_cast<__nv_bfloat16*>(h->q16.p), nqb, h->d, h->d_pad, h->norm_stats,
             reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
             reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p),
-            reinterpret_cast<int*>(h->flags.p), h->sh, nq_pad, h->gstats);
+            reinterpret_cast<int*>(h->flags.p), h->sh, nq_pad, h->gstats,
+            dense_first ? static_cast<int>(first_slab) : 0);
         h->stats.total_launches++;
         CUtensorMap tmap_q;
         RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, TILE_Q));
@@ -460,8 +471,6 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         cp.idesc = use_pair ? IDESC_PAIR[h->sh] : IDESC_SINGLE[h->sh];
 
         int64_t done = 0;
-        int64_t slab = std::min<int64_t>(cap, std::max<int64_t>(1024, 8ll * k));
-        slab = slab / TILE_X * TILE_X;
         long long overflowed = 0;
         // Latency regime (small query batches): a FIXED geometric slab schedule, no host
         // round-trip between slabs.  Growth r is chosen so that ~3k*r expected new hits stay below
@@ -481,6 +490,8 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             cp.x_row0 = done;
             cp.x_row_end = done + s;
             cp.x_tiles = static_cast<int>((s + TILE_X - 1) / TILE_X);
+            cp.dense = (done == 0 && dense_first) ? 1 : 0;
+            const bool last = done + s >= n;
             const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
             cudaEvent_t e0 = get_event(h, ev_used++), e1 = get_event(h, ev_used++);
             CU_TRY(h, cudaEventRecord(e0, h->stream));
@@ -494,17 +505,20 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
                     tmap_q, tmap_x, cp);
             }
             CU_TRY(h, cudaEventRecord(e1, h->stream));
-            refresh_threshold_kernel<<<nqb, SEL_THREADS, 0, h->stream>>>(
-                k, cap, cp.cand, cp.cnt, reinterpret_cast<int*>(h->kept.p),
-                reinterpret_cast<float*>(h->thr.p), reinterpret_cast<float*>(h->eps2.p),
-                reinterpret_cast<int*>(h->flags.p), h->gstats);
+            // the refresh after the LAST slab is fused into the finalize kernel
+            if (!(last && h->fuse_refresh))
+                refresh_threshold_kernel<<<nqb, SEL_THREADS, 0, h->stream>>>(
+                    k, cap, cp.cand, cp.cnt, reinterpret_cast<int*>(h->kept.p),
+                    reinterpret_cast<float*>(h->thr.p), reinterpret_cast<float*>(h->eps2.p),
+                    reinterpret_cast<int*>(h->flags.p), h->gstats);
             cudaEvent_t e2 = get_event(h, ev_used++);
             CU_TRY(h, cudaEventRecord(e2, h->stream));
             h->stats.coarse_launches++;
-            h->stats.total_launches += 2;
+            h->stats.total_launches += (last && h->fuse_refresh) ? 1 : 2;
             h->stats.slabs++;
             h->stats.coarse_flops += 2.0 * nqb * static_cast<double>(s) * h->d;
             done += s;
+            if (last && h->fuse_refresh) break;
             if (fixed_schedule) {
                 slab = std::max<int64_t>(TILE_X, static_cast<int64_t>(static_cast<double>(done) * (growth - 1.0)));
                 if (n - done - slab < slab / 4) slab = n - done;          // no tiny tail slab
@@ -531,7 +545,6 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             next = std::min(next, 4.0e9);
             slab = std::max<int64_t>(TILE_X, static_cast<int64_t>(next));
         }
-        if (!fixed_schedule) h->stats.candidates += h->h_gstats[GS_CANDIDATES];
 
         FinalizeParams fp{};
         fp.k = k; fp.cap = cap; fp.d = h->d;
@@ -545,6 +558,12 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         fp.out_scores = d_scores + q0 * k;
         fp.out_rows = reinterpret_cast<long long*>(d_rows) + q0 * k;
         fp.gstats = h->gstats;
+        if (h->fuse_refresh) {
+            fp.r_cnt = cp.cnt; fp.r_kept = reinterpret_cast<int*>(h->kept.p);
+            fp.r_thr = reinterpret_cast<float*>(h->thr.p);
+            fp.r_eps2 = reinterpret_cast<const float*>(h->eps2.p);
+            fp.r_flags = reinterpret_cast<int*>(h->flags.p);
+        }
         cudaEvent_t f0 = get_event(h->ev_fin, 2 * (h->stats.query_batches - 1));
         cudaEvent_t f1 = get_event(h->ev_fin, 2 * (h->stats.query_batches - 1) + 1);
         CU_TRY(h, cudaEventRecord(f0, h->stream));
@@ -566,25 +585,14 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             CU_TRY(h, cudaStreamSynchronize(h->stream));
         }
         h->stats.rescored += h->h_gstats[GS_RESCORED];
-        if (fixed_schedule) h->stats.candidates += h->h_gstats[GS_CANDIDATES];
+        h->stats.candidates += h->h_gstats[GS_CANDIDATES];
         for (int i = 0; i < static_cast<int>(hflags.size()); i++)
             if (hflags[i] & FLAG_OVERFLOW) fallback.push_back(static_cast<int>(q0 + i));
     }
-    // scoring-kernel time from the recorded event pairs
-    float ms_sum = 0.f, ref_sum = 0.f, fin_sum = 0.f;
-    for (size_t i = 0; i + 3 <= ev_used; i += 3) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]) == cudaSuccess) ms_sum += ms;
-        if (cudaEventElapsedTime(&ms, h->ev_pool[i + 1], h->ev_pool[i + 2]) == cudaSuccess) ref_sum += ms;
-    }
-    for (int b = 0; b < h->stats.query_batches; b++) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->ev_fin[2 * b], h->ev_fin[2 * b + 1]) == cudaSuccess)
-            fin_sum += ms;
-    }
-    h->stats.coarse_ms = ms_sum;
-    h->stats.refresh_ms = ref_sum;
-    h->stats.finalize_ms = fin_sum;
+    // per-kernel times are read from the recorded event pairs lazily, by b2ip_stats (a dozen
+    // cudaEventElapsedTime calls are not free next to a 0.7 ms search)
+    h->timing_events = ev_used;
+    h->timing_pending = true;
     if (h->verbose) {
         float t = 0.f;
         for (size_t i = 0; i + 3 <= ev_used; i += 3) {
@@ -616,6 +624,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
 int search_device(b2ip_handle h, int64_t nq, const float* dq, int k, float* d_scores,
                   int64_t* d_rows, int mode) {
     memset(&h->stats, 0, sizeof(h->stats));
+    h->timing_pending = false;
     h->stats.nq = nq; h->stats.ntotal = h->n; h->stats.k = k;
     if (nq == 0) return B2IP_OK;
     CU_TRY(h, cudaEventRecord(h->ev_t0, h->stream));
@@ -637,9 +646,11 @@ int search_device(b2ip_handle h, int64_t nq, const float* dq, int k, float* d_sc
         CU_TRY(h, cudaStreamSynchronize(h->stream));
     }
     CU_TRY(h, cudaGetLastError());
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
-    h->stats.total_ms = ms;
+    if (h->stats.mode_used != B2IP_MODE_TENSOR || h->n == 0) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
+        h->stats.total_ms = ms;
+    }
     return B2IP_OK;
 }
 
@@ -771,6 +782,8 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "dbg") h->dbg = static_cast<int>(value);
     else if (n == "verbose") h->verbose = static_cast<int>(value);
     else if (n == "pair") h->pair = static_cast<int>(value);
+    else if (n == "dense_first") h->dense_first = static_cast<int>(value);
+    else if (n == "fuse_refresh") h->fuse_refresh = static_cast<int>(value);
     else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;
     else if (n == "shadow_f16") {
         // operand type of the coarse pass of an fp32-stored index; only before the first row
@@ -884,7 +897,7 @@ int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* o
     if (nq >= (1ll << 31)) return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_search: nq too large");
     Guard g(h->device);
     if (mem == B2IP_MEM_DEVICE) return search_device(h, nq, queries, k, out_scores, out_rows, mode);
-    if (nq == 0) { memset(&h->stats, 0, sizeof(h->stats)); return B2IP_OK; }
+    if (nq == 0) { memset(&h->stats, 0, sizeof(h->stats)); h->timing_pending = false; return B2IP_OK; }
     RC_TRY(ensure(h, h->qstage, static_cast<size_t>(nq) * h->d * sizeof(float)));
     RC_TRY(ensure(h, h->out_s, static_cast<size_t>(nq) * k * sizeof(float)));
     RC_TRY(ensure(h, h->out_r, static_cast<size_t>(nq) * k * sizeof(int64_t)));
@@ -982,6 +995,22 @@ int b2ip_copy_to_host(b2ip_handle h, void* dst_host, const void* src_device, int
 
 int b2ip_stats(b2ip_handle h, b2ip_stats_t* out) {
     if (!h || !out) return B2IP_ERR_INVALID;
+    if (h->timing_pending) {
+        Guard g(h->device);
+        float ms_sum = 0.f, ref_sum = 0.f, fin_sum = 0.f, ms = 0.f;
+        for (size_t i = 0; i + 3 <= h->timing_events; i += 3) {
+            if (cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]) == cudaSuccess) ms_sum += ms;
+            if (cudaEventElapsedTime(&ms, h->ev_pool[i + 1], h->ev_pool[i + 2]) == cudaSuccess) ref_sum += ms;
+        }
+        for (int b = 0; b < h->stats.query_batches; b++)
+            if (cudaEventElapsedTime(&ms, h->ev_fin[2 * b], h->ev_fin[2 * b + 1]) == cudaSuccess) fin_sum += ms;
+        if (cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1) == cudaSuccess) h->stats.total_ms = ms;
+        cudaGetLastError();
+        h->stats.coarse_ms = ms_sum;
+        h->stats.refresh_ms = ref_sum;
+        h->stats.finalize_ms = fin_sum;
+        h->timing_pending = false;
+    }
     *out = h->stats;
     return B2IP_OK;
 }
@@ -1004,7 +1033,7 @@ int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev
         queries_dev, reinterpret_cast<__nv_bfloat16*>(h->q16.p), static_cast<int>(nq), h->d, h->d_pad,
         h->norm_stats, reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
         reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p), reinterpret_cast<int*>(h->flags.p), h->sh,
-        static_cast<int>(pad_q(nq)), nullptr);
+        static_cast<int>(pad_q(nq)), nullptr, 0);
     CUtensorMap tmap_q, tmap_x;
     RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nq), h->d_pad, TILE_Q));
     RC_TRY(make_tmap_bf16(h, &tmap_x, h->x16, h->n, h->d_pad, TILE_X));
@@ -1022,6 +1051,7 @@ int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev
     cp.hint_q = hint_policy(h->hint_q);
     cp.hint_x = hint_policy(h->hint_x);
     cp.idesc = IDESC_SINGLE[h->sh];
+    cp.dense = 0;
     const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
     const int grid = static_cast<int>(std::min<long long>(tiles, h->sm_count));
     coarse_filter_kernel<true><<<grid, COARSE_THREADS, COARSE_SMEM_BYTES, h->stream>>>(tmap_q, tmap_x, cp);

@@ -58,6 +58,9 @@ struct CoarseParams {
     float* dump;             // debug: [nq, dump_ld] raw scores, or nullptr
     long long dump_ld;
     unsigned long long hint_q, hint_x;   // L2 eviction-priority policies of the two TMA streams
+    int dense;               // first slab of a search (every threshold is -inf): each column IS a
+                             // hit, stored at list position = row - x_row0 without counters
+                             // (the fill counters are preset to the slab size)
     uint32_t idesc;          // tcgen05 instruction descriptor (IDESC_SINGLE / IDESC_PAIR [format])
     int dbg;                 // perf experiments only (results are wrong when set):
                              // 1 = every tile loads corpus tile 0, 2 = no TMA loads, 4 = no filter
@@ -138,6 +141,36 @@ __device__ __forceinline__ void filter_accumulator(const CoarseParams& p, int q,
                     my_stage[n_staged * 128] = make_key(__uint_as_float(bits), row0 + j);
                     n_staged++;
                 }
+            }
+        }
+    }
+}
+
+// First slab: no threshold exists yet, so every in-range column is a candidate.  Its list
+// position is its row offset inside the slab: no atomics, no hit extraction, 16-byte stores.
+__device__ __forceinline__ void dense_store_accumulator(const CoarseParams& p, int q, uint32_t taddr,
+                                                        long long x_row, int n_valid) {
+    unsigned long long* dst =
+        p.cand + static_cast<long long>(q < p.nq ? q : 0) * p.cap + (x_row - p.x_row0);
+#pragma unroll 1
+    for (int c = 0; c < TILE_X / 32; c++) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (q < p.nq) {
+            const uint32_t row0 = static_cast<uint32_t>(x_row) + c * 32;
+            if (n_valid - c * 32 >= 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    ulonglong2 two;
+                    two.x = make_key(__uint_as_float(v[j]), row0 + j);
+                    two.y = make_key(__uint_as_float(v[j + 1]), row0 + j + 1);
+                    *reinterpret_cast<ulonglong2*>(dst + c * 32 + j) = two;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (c * 32 + j < n_valid) dst[c * 32 + j] = make_key(__uint_as_float(v[j]), row0 + j);
             }
         }
     }
@@ -281,6 +314,8 @@ coarse_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         }
                     }
                 }
+            } else if (p.dense) {
+                dense_store_accumulator(p, q, taddr, x_row, n_valid);
             } else if (!(p.dbg & 4)) {
                 filter_accumulator(p, q, thr, taddr, x_row, n_valid, my_stage, n_staged);
             }
@@ -440,7 +475,8 @@ coarse_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
             ptx::tc_fence_after();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * TILE_X);
-            if (!(p.dbg & 4)) filter_accumulator(p, q, thr, taddr, x_row, n_valid, my_stage, n_staged);
+            if (p.dense) dense_store_accumulator(p, q, taddr, x_row, n_valid);
+            else if (!(p.dbg & 4)) filter_accumulator(p, q, thr, taddr, x_row, n_valid, my_stage, n_staged);
             ptx::tc_fence_before();
             ptx::mbar_arrive_cluster(as == 0 ? tempty_leader0 : tempty_leader1);
             if (++as == 2) { as = 0; aphase ^= 1; }

@@ -17,6 +17,7 @@ namespace b2ip {
 constexpr int SEL_THREADS = 256;
 constexpr int SORT_CAP = 4096;       // u64 keys sorted in shared memory by finalize
 constexpr int REFRESH_SMEM_KEYS = 4096;   // candidate lists up to this size are refreshed from smem
+static_assert(REFRESH_SMEM_KEYS <= SORT_CAP, "finalize stages the fused refresh in its sort buffer");
 constexpr int FLAG_OVERFLOW = 1;
 constexpr int EXACT_QB = 8;          // queries per pass of the exact path
 
@@ -194,7 +195,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
                                     float* __restrict__ eps2, float* __restrict__ thr,
                                     int* __restrict__ cnt, int* __restrict__ kept,
                                     int* __restrict__ flags, int sh, int nq_pad,
-                                    long long* __restrict__ gstats) {
+                                    long long* __restrict__ gstats, int init_cnt) {
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x < GS_COUNT && gstats) gstats[threadIdx.x] = 0;
@@ -235,7 +236,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
         if (!(e <= FLT_MAX)) e = INFINITY;
         eps2[q] = 2.f * e;
         thr[q] = -INFINITY;
-        cnt[q] = 0;
+        cnt[q] = init_cnt;                 // rows of the dense first slab (stored without counters)
         kept[q] = 0;
         flags[q] = 0;
     }
@@ -385,19 +386,19 @@ __device__ int block_compact_disjoint(const unsigned long long* keys, int n, boo
 // Let c_k be the k-th largest COARSE score seen so far.  k rows have exact score >= c_k - eps,
 // so every member of the final exact top-k has exact >= c_k - eps and coarse >= c_k - 2 eps:
 // rows below that can be dropped for good, and later slabs only need to report above it.
-__global__ void __launch_bounds__(SEL_THREADS)
-refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
-                         int* __restrict__ cnt, int* __restrict__ kept, float* __restrict__ thr,
-                         const float* __restrict__ eps2, int* __restrict__ flags,
-                         long long* __restrict__ gstats) {
-    __shared__ unsigned int hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ int s_krem;
-    __shared__ int s_warp[SEL_THREADS / 32];
-    const int q = blockIdx.x;
-    if (flags[q] & FLAG_OVERFLOW) return;
+// Returns the number of entries the list holds afterwards (block-uniform), or -1 when the query
+// overflowed its list (flagged for the exact path).  `scratch` = REFRESH_SMEM_KEYS keys of
+// shared memory: lists that fit are pulled into it once, so the 4 select passes and the
+// compaction never touch L2 again.
+__device__ int refresh_list(int q, int k, int cap, unsigned long long* __restrict__ cand,
+                            int* __restrict__ cnt, int* __restrict__ kept, float* __restrict__ thr,
+                            const float* __restrict__ eps2, int* __restrict__ flags,
+                            long long* __restrict__ gstats, unsigned long long* scratch,
+                            unsigned int* hist, unsigned long long* s_prefix, int* s_krem,
+                            int* s_warp) {
     const int n = cnt[q];
     const int prev = kept[q];
+    __syncthreads();                                 // everyone has read the counters
     if (n > cap) {
         // more hits than the list holds: this query is re-run on the exact path
         if (threadIdx.x == 0) {
@@ -407,27 +408,24 @@ refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
             kept[q] = 0;
             atomicAdd(reinterpret_cast<unsigned long long*>(gstats + GS_OVERFLOW), 1ull);
         }
-        return;
+        return -1;
     }
-    if (n == prev) return;
+    if (n == prev) return n;
     if (threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(gstats + GS_CANDIDATES),
                   static_cast<unsigned long long>(n - prev));
     if (n < k) {
         if (threadIdx.x == 0) kept[q] = n;
-        return;
+        return n;
     }
     unsigned long long* keys = cand + static_cast<long long>(q) * cap;
-    // lists that fit are pulled into shared memory once: the 4 select passes and the
-    // compaction then never touch L2 again
-    __shared__ unsigned long long skeys[REFRESH_SMEM_KEYS];
     const unsigned long long* src = keys;
     if (n <= REFRESH_SMEM_KEYS) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[i] = keys[i];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) scratch[i] = keys[i];
         __syncthreads();
-        src = skeys;
+        src = scratch;
     }
-    const unsigned long long pk = block_radix_select(src, n, k, 4, hist, &s_prefix, &s_krem);
+    const unsigned long long pk = block_radix_select(src, n, k, 4, hist, s_prefix, s_krem);
     const float ck = unorder_f32(static_cast<uint32_t>(pk >> 32));
     float t = __fsub_rd(ck, eps2[q]);
     if (!(t == t)) t = -INFINITY;                    // inf - inf: no usable threshold
@@ -441,6 +439,23 @@ refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
         atomicMax(reinterpret_cast<unsigned long long*>(gstats + GS_MAX_KEPT),
                   static_cast<unsigned long long>(m));
     }
+    return m;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
+                         int* __restrict__ cnt, int* __restrict__ kept, float* __restrict__ thr,
+                         const float* __restrict__ eps2, int* __restrict__ flags,
+                         long long* __restrict__ gstats) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_krem;
+    __shared__ int s_warp[SEL_THREADS / 32];
+    __shared__ unsigned long long skeys[REFRESH_SMEM_KEYS];
+    const int q = blockIdx.x;
+    if (flags[q] & FLAG_OVERFLOW) return;
+    refresh_list(q, k, cap, cand, cnt, kept, thr, eps2, flags, gstats, skeys, hist, &s_prefix,
+                 &s_krem, s_warp);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -452,6 +467,9 @@ struct FinalizeParams {
     unsigned long long* cand;         // [slots, cap]
     const int* cnt;                   // [slots] entries per slot
     const int* flags;                 // [slots] or nullptr
+    // fused last threshold refresh (tensor path; nullptr otherwise): the raw fill counters, the
+    // kept counts, thresholds, bounds and flags the refresh kernel would have updated
+    int* r_cnt; int* r_kept; float* r_thr; const float* r_eps2; int* r_flags;
     const float* q32;                 // [*, d] fp32 queries (rescore)
     const float* x32;                 // [n, d] fp32 corpus (rescore), or nullptr:
     const __nv_bfloat16* x16;         // [n, d_pad] 16-bit corpus when the index stores bf16 / fp16
@@ -491,7 +509,17 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
     const int slot = blockIdx.x;
     if (p.flags && (p.flags[slot] & FLAG_OVERFLOW)) return;
     const int q = p.qlist ? p.qlist[slot] : slot;
-    const int n = min(p.cnt[slot], p.cap);
+    int n;
+    if (kRescore && p.r_cnt) {
+        // the refresh that would follow the last slab, done here: one launch and one pass over
+        // the list less (sbuf doubles as its staging area: SORT_CAP == REFRESH_SMEM_KEYS)
+        n = refresh_list(slot, p.k, p.cap, p.cand, p.r_cnt, p.r_kept, p.r_thr, p.r_eps2, p.r_flags,
+                         p.gstats, sbuf, hist, &s_prefix, &s_krem, s_warp);
+        if (n < 0) return;
+        __syncthreads();                             // compacted list visible to every warp
+    } else {
+        n = min(p.cnt[slot], p.cap);
+    }
     unsigned long long* keys = p.cand + static_cast<long long>(slot) * p.cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
