@@ -21,7 +21,7 @@ MAX_K = 2048
 # every symbol include/b2ip.h declares (tests check the .so exports all of them)
 SYMBOLS = (
     "b2ip_create", "b2ip_create_ex", "b2ip_destroy", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_ntotal",
-    "b2ip_dim", "b2ip_set_row_offset", "b2ip_search", "b2ip_merge_topk", "b2ip_merge_topk_strided", "b2ip_export_rows",
+    "b2ip_dim", "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_exchange", "b2ip_merge_topk", "b2ip_merge_topk_strided", "b2ip_export_rows",
     "b2ip_copy_to_device", "b2ip_copy_to_host", "b2ip_stats", "b2ip_last_error", "b2ip_debug_coarse_scores", "b2ip_version",
 )
 
@@ -41,6 +41,15 @@ class Stats(ctypes.Structure):
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+MAX_PEERS = 8
+
+
+class Exchange(ctypes.Structure):
+    """b2ip_exchange_t (include/b2ip.h): peer-mapped gather buffers and flag arrays of one parity."""
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("slot_bytes", ctypes.c_int64),
+                ("gather", ctypes.c_void_p * MAX_PEERS), ("flags", ctypes.c_void_p * MAX_PEERS)]
 
 
 class B2ipError(RuntimeError):
@@ -76,7 +85,10 @@ def load() -> ctypes.CDLL:
     lib.b2ip_ntotal.restype = i64
     lib.b2ip_dim.argtypes = [vp]
     lib.b2ip_set_row_offset.argtypes = [vp, i64]
+    lib.b2ip_set_row_segments.argtypes = [vp, i32, vp, vp]
     lib.b2ip_search.argtypes = [vp, i64, vp, i32, vp, vp, i32, i32]
+    lib.b2ip_search_exchange.argtypes = [vp, i64, vp, i32, ctypes.POINTER(Exchange), ctypes.c_uint32, vp, vp,
+                                         ctypes.POINTER(ctypes.c_int64)]
     lib.b2ip_merge_topk.argtypes = [i32, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.b2ip_merge_topk_strided.argtypes = [i32, vp, i64, i32, i32, vp, vp, i64, i64, vp, vp]
     lib.b2ip_export_rows.argtypes = [vp, i64, i64, vp, i32]
@@ -88,7 +100,7 @@ def load() -> ctypes.CDLL:
     lib.b2ip_debug_coarse_scores.argtypes = [vp, i64, vp, i64, i64, vp]
     lib.b2ip_version.restype = ctypes.c_char_p
     for name in ("b2ip_create", "b2ip_create_ex", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_dim",
-                 "b2ip_set_row_offset", "b2ip_search", "b2ip_merge_topk", "b2ip_merge_topk_strided",
+                 "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_exchange", "b2ip_merge_topk", "b2ip_merge_topk_strided",
                  "b2ip_export_rows", "b2ip_stats", "b2ip_debug_coarse_scores", "b2ip_copy_to_device",
                  "b2ip_copy_to_host"):
         getattr(lib, name).restype = i32

@@ -73,6 +73,18 @@ class Engine:
     def set_row_offset(self, offset: int) -> None:
         check(self._lib.b2ip_set_row_offset(self._h, int(offset)), self._h)
 
+    def set_row_segments(self, segments) -> None:
+        """segments: [(local_start, global_start, n), ...] in increasing order; the engine then
+        reports GLOBAL row ids itself (one segment: a plain offset)."""
+        if len(segments) <= 1:
+            check(self._lib.b2ip_set_row_segments(self._h, 0, None, None), self._h)
+            self.set_row_offset(segments[0][1] - segments[0][0] if segments else 0)
+            return
+        ls = np.ascontiguousarray([s[0] for s in segments], dtype=np.int64)
+        gs = np.ascontiguousarray([s[1] for s in segments], dtype=np.int64)
+        check(self._lib.b2ip_set_row_segments(self._h, len(segments), ctypes.c_void_p(ls.ctypes.data),
+                                              ctypes.c_void_p(gs.ctypes.data)), self._h)
+
     @property
     def ntotal(self) -> int:
         return int(self._lib.b2ip_ntotal(self._h))
@@ -145,6 +157,24 @@ class Engine:
                                     ctypes.c_void_p(D.ctypes.data), ctypes.c_void_p(I.ctypes.data),
                                     m, MEM_HOST), self._h)
         return D, I
+
+    def search_exchange(self, queries, k: int, ex, seq: int):
+        """Local search + peer-direct exchange + merge in one call (b2ip_search_exchange).
+        `ex`: _lib.Exchange of this parity.  Returns (D, I, status): the GLOBAL top-k on this
+        rank's device and the number of overflowed queries over all ranks (non-zero: repeat the
+        search through the all-gather path)."""
+        import torch
+        q = queries.float().contiguous()
+        assert q.is_cuda and q.device.index == self.device and q.dim() == 2 and q.shape[1] == self.d
+        nq, k = q.shape[0], int(k)
+        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        status = ctypes.c_int64(0)
+        torch.cuda.current_stream(self.device).synchronize()
+        check(self._lib.b2ip_search_exchange(self._h, nq, ctypes.c_void_p(q.data_ptr()), k, ctypes.byref(ex),
+                                             ctypes.c_uint32(seq & 0xFFFFFFFF), ctypes.c_void_p(D.data_ptr()),
+                                             ctypes.c_void_p(I.data_ptr()), ctypes.byref(status)), self._h)
+        return D, I, int(status.value)
 
     def upload(self, dst, src: np.ndarray) -> None:
         """dst (torch CUDA tensor on this engine's device) <- src (host array of the same byte

@@ -140,8 +140,7 @@ class MultiGpuEngine:
         for j in jobs:
             j.result()
         for g, e in enumerate(self.engines):
-            off = self.maps[g].single_offset()
-            e.set_row_offset(off if off is not None else 0)
+            e.set_row_segments(self.maps[g].segments)      # the engine reports global ids itself
         self._n += n
 
     def _add_one(self, g: int, part) -> None:
@@ -165,8 +164,6 @@ class MultiGpuEngine:
         with torch.cuda.device(dev):
             q = q_dev0 if q_dev0.device == dev else q_dev0.to(dev)      # fan-out over NVLink
             D, I = self.engines[g].search(q, k, mode=mode)
-            if self.maps[g].single_offset() is None:
-                I = self.maps[g].to_global(I)
             st = self.engines[g].stats()
             torch.cuda.current_stream(dev).synchronize()
         return D, I, st

@@ -3,11 +3,19 @@ owns a set of corpus segments in its own `Engine`, queries are replicated, every
 a local top-k and the one exchange step is an all-gather of the [nq,k] (score, global row)
 blocks over NCCL/NVLink followed by the merge kernel.
 
+With `peer_exchange` (default when torch symmetric memory can map the ranks' buffers into each
+other, i.e. on one NVLink/NVSwitch box) the exchange is fused behind the search instead: the
+engine's finalize kernel stores every rank's block straight into all peers' gather buffers over
+NVLink, a flag is published, and each rank's merge kernel starts as soon as all flags are in
+(`b2ip_search_exchange`, include/b2ip.h) -- no NCCL call and no host round trip between the
+local search and the merge, which is what the latency regime (BASELINE config 5) is made of.
+
 The reference runs this path in a single process on host cores (faiss OpenMP,
 src/index.py:42); sharding is how the same search is spread over 1/2/4/8 B200s.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Tuple
 
 
@@ -19,8 +27,11 @@ def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 class ShardedIndex:
+    FLAG_BYTES = 256          # per parity: uint32[2 * world] flags, padded
+
     def __init__(self, d: int, device: Optional[int] = None, engine=None, group=None,
-                 merge_fn: Optional[Callable] = None, store: str = "f32"):
+                 merge_fn: Optional[Callable] = None, store: str = "f32",
+                 peer_exchange: Optional[bool] = None):
         import torch
         import torch.distributed as dist
         self._torch, self._dist = torch, dist
@@ -43,6 +54,15 @@ class ShardedIndex:
         self._n_seen = 0          # add_replicated: rows seen by every rank so far
         self._chunk_no = 0
         self._seg_cache = None
+        if peer_exchange is None:
+            peer_exchange = os.environ.get("B2IP_PEER_EXCHANGE", "1") != "0"
+        self.peer_exchange = bool(peer_exchange) and self.world > 1 and self.world <= 8 \
+            and self._engine_writes_in_place()
+        self._x_buf = None        # symmetric buffer [2 parities x world slots | 2 flag arrays]
+        self._x_slot = 0
+        self._x_ex = None
+        self._x_seq = 0
+        self.exchange_searches = 0
 
     # -- ingest ----------------------------------------------------------------------
     def add_local(self, rows, global_start: int) -> None:
@@ -61,8 +81,11 @@ class ShardedIndex:
             self.segments.append((self._n_local, int(global_start), n))
         self._n_local += n
         self._seg_cache = None
-        # one contiguous segment: the engine adds the offset itself (no extra kernels per search)
-        if hasattr(self.engine, "set_row_offset"):
+        # the engine maps local rows to global ids itself (offset or segment table): no extra
+        # kernels per search, and its results can go straight to the peers
+        if hasattr(self.engine, "set_row_segments"):
+            self.engine.set_row_segments(self.segments)
+        elif hasattr(self.engine, "set_row_offset"):
             self.engine.set_row_offset(self.segments[0][1] - self.segments[0][0]
                                        if len(self.segments) == 1 else 0)
 
@@ -82,8 +105,8 @@ class ShardedIndex:
     # -- search ----------------------------------------------------------------------
     def _to_global(self, rows_local):
         torch = self._torch
-        if not self.segments:
-            return rows_local
+        if not self.segments or hasattr(self.engine, "set_row_segments"):
+            return rows_local                          # already global
         if len(self.segments) == 1:
             if hasattr(self.engine, "set_row_offset"):
                 return rows_local                      # offset already applied by the engine
@@ -104,14 +127,59 @@ class ShardedIndex:
 
     def search(self, queries, k: int, mode: str = "auto"):
         """queries: [nq,d] tensor on this rank's device (identical on all ranks).
-        Returns the global (scores [nq,k], rows [nq,k]) on every rank.
+        Returns the global (scores [nq,k], rows [nq,k]) on every rank."""
+        if self.world == 1:
+            return self.search_local(queries, k, mode)
+        if self.peer_exchange and mode != "exact" and int(queries.shape[0]) > 0:
+            ex = self._exchange_buffers(int(queries.shape[0]), int(k))
+            self._x_seq += 1
+            D, I, status = self.engine.search_exchange(queries, k, ex[self._x_seq & 1], self._x_seq)
+            if status == 0:
+                self.exchange_searches += 1
+                return D, I
+            # some rank overflowed a candidate list (same status everywhere): all ranks repeat
+            # the search below, where the exact fallback runs before the exchange
+        return self._search_allgather(queries, k, mode)
 
-        One exchange step: every rank owns a slot [rows int64 | scores fp32] of ONE packed
+    # -- peer-direct exchange --------------------------------------------------------
+    def _exchange_buffers(self, nq: int, k: int):
+        """Symmetric (peer-mapped) gather buffers + flag arrays, two parities; grown collectively."""
+        need = (nq * k * 12 + 15) // 16 * 16
+        if self._x_ex is not None and need <= self._x_slot:
+            return self._x_ex
+        import torch.distributed._symmetric_memory as symm_mem
+        from ._lib import Exchange
+        torch, dist = self._torch, self._dist
+        dev = torch.device("cuda", self.engine.device)
+        slot = 1 << 12
+        while slot < need:
+            slot <<= 1
+        total = 2 * self.world * slot + 2 * self.FLAG_BYTES
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)                 # nobody still uses the old buffers
+        buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        buf.zero_()
+        torch.cuda.synchronize(dev)
+        hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        hdl.barrier()                                  # every rank's flags are zero before any write
+        ptrs = list(hdl.buffer_ptrs)
+        exs = []
+        for parity in (0, 1):
+            ex = Exchange()
+            ex.world, ex.rank, ex.slot_bytes = self.world, self.rank, slot
+            for p in range(self.world):
+                ex.gather[p] = ptrs[p] + parity * self.world * slot
+                ex.flags[p] = ptrs[p] + 2 * self.world * slot + parity * self.FLAG_BYTES
+            exs.append(ex)
+        self._x_buf, self._x_hdl, self._x_slot, self._x_ex, self._x_seq = buf, hdl, slot, exs, 0
+        return exs
+
+    # -- all-gather exchange -----------------------------------------------------------
+    def _search_allgather(self, queries, k: int, mode: str = "auto"):
+        """One exchange step: every rank owns a slot [rows int64 | scores fp32] of ONE packed
         buffer, the engine writes its local top-k straight into its slot, a single in-place
         all-gather fills the others, and the merge kernel reads the slots where they are."""
         torch, dist = self._torch, self._dist
-        if self.world == 1:
-            return self.search_local(queries, k, mode)
         nq = int(queries.shape[0])
         nb = nq * k
         slot = (nb * 12 + 15) // 16 * 16

@@ -73,7 +73,8 @@ struct b2ip_index_s {
     PFN_encodeTiled encode = nullptr;
     // grow-only workspace
     DevBuf q16, eps2, thr, cnt, kept, flags, cand, qstage, out_s, out_r, exact_scores, exact_misc,
-        qlist, stage;
+        qlist, stage, seg_tab;
+    int n_seg = 0;                        // row segments (b2ip_set_row_segments); 0 = row_offset
     std::vector<cudaEvent_t> ev_pool, ev_fin;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     b2ip_stats_t stats;
@@ -87,6 +88,14 @@ struct b2ip_index_s {
     int fuse_refresh = 1;                 // last threshold refresh inside the finalize kernel
     long long cand_budget_bytes = 6ll << 30;
     CUtensorMap tmap_x, tmap_x_pair;      // cached TMA descriptors of x16 (single / pair box)
+    // peer-direct exchange of the current b2ip_search_exchange call (n_extra == 0 otherwise)
+    int n_extra = 0;
+    char* extra_base[MAX_PEERS - 1] = {};   // peer slots for this rank's results: [rows | scores]
+    const b2ip_exchange_t* ex = nullptr;
+    unsigned int ex_seq = 0;
+    long long ex_prior_overflow = 0;      // overflowed queries of earlier query batches of this search
+    float* ex_out_s = nullptr;
+    int64_t* ex_out_r = nullptr;
     size_t timing_events = 0;             // event triples of the last tensor search (read by b2ip_stats)
     bool timing_pending = false;
     const void* tmap_x_base = nullptr;
@@ -391,12 +400,42 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
         fp.cnt = gcnt; fp.flags = nullptr; fp.q32 = q32; fp.x32 = h->x32;
         fp.x16 = h->x16; fp.d_pad = h->d_pad; fp.sh = h->sh;
         fp.row_offset = h->row_offset;
+        fp.n_seg = h->n_seg;
+        fp.seg_local = static_cast<const long long*>(h->seg_tab.p);
+        fp.seg_delta = fp.seg_local + h->n_seg;
         fp.out_scores = d_scores; fp.out_rows = reinterpret_cast<long long*>(d_rows);
         fp.gstats = nullptr;
+        fp.n_extra = 0;
         finalize_kernel<false><<<nqg, SEL_THREADS, fin_smem, h->stream>>>(fp);
         h->stats.total_launches += 20;
     }
     CU_TRY(h, cudaGetLastError());
+    return B2IP_OK;
+}
+
+// ------------------------------------------------------------------------- peer-direct exchange
+// After the last finalize of a search: tell every rank that this rank's [nq,k] block is in its
+// memory, then merge the world's blocks out of THIS rank's gather buffer as soon as all flags are
+// in.  Two launches behind finalize on the same stream -- no host round trip, no NCCL call.
+int enqueue_exchange(b2ip_handle h, int64_t nq, int k) {
+    const b2ip_exchange_t* ex = h->ex;
+    PeerFlags pf{};
+    pf.world = ex->world;
+    pf.rank = ex->rank;
+    for (int p = 0; p < ex->world; p++) pf.flags[p] = static_cast<unsigned int*>(ex->flags[p]);
+    exchange_signal_kernel<<<1, 32, 0, h->stream>>>(pf, h->ex_seq, h->gstats, h->ex_prior_overflow);
+    int P = 2;
+    while (P < ex->world * k) P <<= 1;
+    const size_t smem = static_cast<size_t>(P) * sizeof(unsigned long long);
+    if (smem > 200 * 1024) return fail(h, B2IP_ERR_UNSUPPORTED, "exchange: world*k=%d too large", ex->world * k);
+    CU_TRY(h, cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const char* mine = static_cast<const char*>(ex->gather[ex->rank]);
+    merge_topk_kernel<<<static_cast<unsigned int>(nq), SEL_THREADS, smem, h->stream>>>(
+        nq, k, ex->world, reinterpret_cast<const float*>(mine + static_cast<size_t>(nq) * k * 8),
+        reinterpret_cast<const long long*>(mine), ex->slot_bytes / 4, ex->slot_bytes / 8, h->ex_out_s,
+        reinterpret_cast<long long*>(h->ex_out_r), P, static_cast<const unsigned int*>(ex->flags[ex->rank]),
+        h->ex_seq, h->gstats + GS_XSTATUS);
+    h->stats.total_launches += 2;
     return B2IP_OK;
 }
 
@@ -555,9 +594,17 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         fp.q32 = qptr; fp.x32 = h->x32;
         fp.x16 = h->x16; fp.d_pad = h->d_pad; fp.sh = h->sh;
         fp.row_offset = h->row_offset;
+        fp.n_seg = h->n_seg;
+        fp.seg_local = static_cast<const long long*>(h->seg_tab.p);
+        fp.seg_delta = fp.seg_local + h->n_seg;
         fp.out_scores = d_scores + q0 * k;
         fp.out_rows = reinterpret_cast<long long*>(d_rows) + q0 * k;
         fp.gstats = h->gstats;
+        fp.n_extra = h->n_extra;
+        for (int e = 0; e < h->n_extra; e++) {
+            fp.extra_r[e] = reinterpret_cast<long long*>(h->extra_base[e]) + q0 * k;
+            fp.extra_s[e] = reinterpret_cast<float*>(h->extra_base[e] + static_cast<size_t>(nq) * k * 8) + q0 * k;
+        }
         if (h->fuse_refresh) {
             fp.r_cnt = cp.cnt; fp.r_kept = reinterpret_cast<int*>(h->kept.p);
             fp.r_thr = reinterpret_cast<float*>(h->thr.p);
@@ -572,6 +619,10 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         h->stats.total_launches++;
         // end of the device-side search (re-recorded after the exact fallback, if any): the
         // D2H of the counters below and ONE host synchronisation finish the call
+        if (q0 + qb >= nq && h->ex) {
+            h->ex_prior_overflow = static_cast<long long>(fallback.size());
+            RC_TRY(enqueue_exchange(h, nq, k));
+        }
         if (q0 + qb >= nq) CU_TRY(h, cudaEventRecord(h->ev_t1, h->stream));
         CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
                                   cudaMemcpyDeviceToHost, h->stream));
@@ -611,7 +662,11 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             fprintf(stderr, "[b2ip] t=%.3f ms: finalize %.3f (last slab ended at %.3f)\n", a, f, t);
         }
     }
-    if (!fallback.empty()) {
+    if (!fallback.empty() && h->ex) {
+        // peers have already merged what finalize stored: the caller sees a non-zero exchange
+        // status on every rank and repeats the search through the all-gather path
+        h->stats.fallback_queries = static_cast<int64_t>(fallback.size());
+    } else if (!fallback.empty()) {
         h->stats.fallback_queries = static_cast<int64_t>(fallback.size());
         RC_TRY(exact_search(h, q32, fallback.data(), static_cast<int64_t>(fallback.size()), k,
                             d_scores, d_rows));
@@ -632,6 +687,17 @@ int search_device(b2ip_handle h, int64_t nq, const float* dq, int k, float* d_sc
         fill_padding_kernel<<<256, 256, 0, h->stream>>>(d_scores, reinterpret_cast<long long*>(d_rows), nq * k);
         h->stats.total_launches = 1;
         h->stats.mode_used = B2IP_MODE_EXACT;
+        if (h->ex) {      // an empty shard still takes part in the peer-direct exchange
+            for (int e = 0; e < h->n_extra; e++)
+                fill_padding_kernel<<<256, 256, 0, h->stream>>>(
+                    reinterpret_cast<float*>(h->extra_base[e] + static_cast<size_t>(nq) * k * 8),
+                    reinterpret_cast<long long*>(h->extra_base[e]), nq * k);
+            CU_TRY(h, cudaMemsetAsync(h->gstats, 0, GS_COUNT * sizeof(long long), h->stream));
+            h->ex_prior_overflow = 0;
+            RC_TRY(enqueue_exchange(h, nq, k));
+            CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
+                                      cudaMemcpyDeviceToHost, h->stream));
+        }
     } else if (mode == B2IP_MODE_EXACT) {
         h->stats.mode_used = B2IP_MODE_EXACT;
         std::vector<int> all(nq);
@@ -747,7 +813,8 @@ void b2ip_destroy(b2ip_handle h) {
     Guard g(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (DevBuf* b : {&h->q16, &h->eps2, &h->thr, &h->cnt, &h->kept, &h->flags, &h->cand, &h->qstage,
-                      &h->out_s, &h->out_r, &h->exact_scores, &h->exact_misc, &h->qlist, &h->stage})
+                      &h->out_s, &h->out_r, &h->exact_scores, &h->exact_misc, &h->qlist, &h->stage,
+                      &h->seg_tab})
         release(*b);
     if (h->x32) cudaFree(h->x32);
     if (h->x16) cudaFree(h->x16);
@@ -885,6 +952,32 @@ int b2ip_set_row_offset(b2ip_handle h, int64_t offset) {
     return B2IP_OK;
 }
 
+int b2ip_set_row_segments(b2ip_handle h, int n_segments, const int64_t* local_start,
+                          const int64_t* global_start) {
+    if (!h || n_segments < 0 || (n_segments > 0 && (!local_start || !global_start)))
+        return fail(h, B2IP_ERR_INVALID, "b2ip_set_row_segments: bad arguments");
+    for (int i = 0; i < n_segments; i++) {
+        if (local_start[i] < 0 || global_start[i] < 0 || (i == 0 && local_start[0] != 0) ||
+            (i > 0 && (local_start[i] <= local_start[i - 1] || global_start[i] <= global_start[i - 1])))
+            return fail(h, B2IP_ERR_INVALID, "b2ip_set_row_segments: segment %d out of order", i);
+    }
+    Guard g(h->device);
+    if (n_segments > 0) {
+        std::vector<long long> tab(2 * static_cast<size_t>(n_segments));
+        for (int i = 0; i < n_segments; i++) {
+            tab[i] = local_start[i];
+            tab[n_segments + i] = global_start[i] - local_start[i];
+        }
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        RC_TRY(ensure(h, h->seg_tab, tab.size() * sizeof(long long)));
+        CU_TRY(h, cudaMemcpyAsync(h->seg_tab.p, tab.data(), tab.size() * sizeof(long long),
+                                  cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    h->n_seg = n_segments;
+    return B2IP_OK;
+}
+
 int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* out_scores,
                 int64_t* out_rows, int mode, int mem) {
     if (!h) return B2IP_ERR_INVALID;
@@ -920,6 +1013,40 @@ int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* o
     return B2IP_OK;
 }
 
+int b2ip_search_exchange(b2ip_handle h, int64_t nq, const float* queries_dev, int k,
+                         const b2ip_exchange_t* ex, uint32_t seq, float* out_scores_dev,
+                         int64_t* out_rows_dev, int64_t* status) {
+    if (!h) return B2IP_ERR_INVALID;
+    if (!ex || !status || nq <= 0 || !queries_dev || !out_scores_dev || !out_rows_dev)
+        return fail(h, B2IP_ERR_INVALID, "b2ip_search_exchange: NULL argument or nq=%lld", (long long)nq);
+    if (k < 1 || k > B2IP_MAX_K) return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_search_exchange: k=%d", k);
+    if (ex->world < 1 || ex->world > B2IP_MAX_PEERS || ex->rank < 0 || ex->rank >= ex->world)
+        return fail(h, B2IP_ERR_INVALID, "b2ip_search_exchange: world=%d rank=%d", ex->world, ex->rank);
+    if (ex->slot_bytes % 16 != 0 || ex->slot_bytes < nq * k * 12)
+        return fail(h, B2IP_ERR_INVALID, "b2ip_search_exchange: slot_bytes=%lld for nq*k=%lld", (long long)ex->slot_bytes, (long long)(nq * k));
+    Guard g(h->device);
+    // this rank's block goes to slot `rank` of every rank's gather buffer; the local one is the
+    // primary output of the finalize kernel, the others its extra (peer) outputs
+    char* mine = static_cast<char*>(ex->gather[ex->rank]) + static_cast<size_t>(ex->rank) * ex->slot_bytes;
+    h->n_extra = 0;
+    for (int p = 0; p < ex->world; p++)
+        if (p != ex->rank)
+            h->extra_base[h->n_extra++] = static_cast<char*>(ex->gather[p]) + static_cast<size_t>(ex->rank) * ex->slot_bytes;
+    h->ex = ex;
+    h->ex_seq = seq;
+    h->ex_out_s = out_scores_dev;
+    h->ex_out_r = out_rows_dev;
+    const int rc = search_device(h, nq, queries_dev, k, reinterpret_cast<float*>(mine + static_cast<size_t>(nq) * k * 8),
+                                 reinterpret_cast<int64_t*>(mine), B2IP_MODE_TENSOR);
+    h->ex = nullptr;
+    h->n_extra = 0;
+    if (rc != B2IP_OK) return rc;
+    *status = h->h_gstats[GS_XSTATUS];
+    if (*status >= XSTATUS_TIMEOUT)
+        return fail(h, B2IP_ERR_INTERNAL, "b2ip_search_exchange: a peer's results never arrived (seq %u)", seq);
+    return B2IP_OK;
+}
+
 int b2ip_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int n_lists,
                     const float* scores, const int64_t* rows, float* out_scores, int64_t* out_rows) {
     return b2ip_merge_topk_strided(device, cuda_stream, nq, k, n_lists, scores, rows, nq * k, nq * k,
@@ -943,7 +1070,7 @@ int b2ip_merge_topk_strided(int device, void* cuda_stream, int64_t nq, int k, in
     if (e == cudaSuccess) {
         merge_topk_kernel<<<static_cast<unsigned int>(nq), SEL_THREADS, smem, st>>>(
             nq, k, n_lists, scores, reinterpret_cast<const long long*>(rows), scores_list_stride,
-            rows_list_stride, out_scores, reinterpret_cast<long long*>(out_rows), P);
+            rows_list_stride, out_scores, reinterpret_cast<long long*>(out_rows), P, nullptr, 0u, nullptr);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -22,7 +22,9 @@ constexpr int FLAG_OVERFLOW = 1;
 constexpr int EXACT_QB = 8;          // queries per pass of the exact path
 
 // device-side counters of one search (int64 each)
-enum { GS_MAX_KEPT = 0, GS_OVERFLOW = 1, GS_CANDIDATES = 2, GS_RESCORED = 3, GS_COUNT = 4 };
+enum { GS_MAX_KEPT = 0, GS_OVERFLOW = 1, GS_CANDIDATES = 2, GS_RESCORED = 3, GS_XSTATUS = 4, GS_COUNT = 5 };
+constexpr int MAX_PEERS = 8;         // ranks of one NVSwitch box in the peer-direct exchange
+constexpr long long XSTATUS_TIMEOUT = 1ll << 40;   // GS_XSTATUS: a peer's flag never arrived
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -475,9 +477,17 @@ struct FinalizeParams {
     const __nv_bfloat16* x16;         // [n, d_pad] 16-bit corpus when the index stores bf16 / fp16
     int d_pad;
     int sh;                           // SH_BF16 / SH_F16: element type of x16
-    long long row_offset;
+    long long row_offset;             // reported id = local row + row_offset, or (n_seg > 0):
+    int n_seg;                        // local row + seg_delta[s], s = last segment with
+    const long long* seg_local;       // seg_local[s] <= local row (shards made of several
+    const long long* seg_delta;       // global row ranges)
     float* out_scores;                // [*, k]
     long long* out_rows;              // [*, k]
+    // peer-direct exchange: the same results are also stored into these buffers, which live in
+    // the OTHER GPUs' memory (NVLink P2P stores), so no separate all-gather is needed
+    int n_extra;
+    float* extra_s[MAX_PEERS - 1];
+    long long* extra_r[MAX_PEERS - 1];
     long long* gstats;
 };
 
@@ -582,10 +592,28 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
         long long r = -1;
         if (j < m) {
             const unsigned long long key = sbuf[j];
-            if ((key >> 32) != 0ull) { s = key_score(key); r = static_cast<long long>(key_row(key)) + p.row_offset; }
+            if ((key >> 32) != 0ull) {
+                s = key_score(key);
+                r = static_cast<long long>(key_row(key));
+                if (p.n_seg > 0) {
+                    int lo = 0, hi = p.n_seg - 1;          // last segment starting at or before r
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (p.seg_local[mid] <= r) lo = mid; else hi = mid - 1;
+                    }
+                    r += p.seg_delta[lo];
+                } else {
+                    r += p.row_offset;
+                }
+            }
         }
-        p.out_scores[static_cast<long long>(q) * p.k + j] = s;
-        p.out_rows[static_cast<long long>(q) * p.k + j] = r;
+        const long long o = static_cast<long long>(q) * p.k + j;
+        p.out_scores[o] = s;
+        p.out_rows[o] = r;
+        for (int e = 0; e < p.n_extra; e++) {
+            p.extra_s[e][o] = s;
+            p.extra_r[e][o] = r;
+        }
     }
 }
 
@@ -723,6 +751,26 @@ exact_collect_kernel(const float* __restrict__ scores, long long n, const ExactS
 }
 
 // ---------------------------------------------------------------------------------------
+// peer-direct exchange: publish "my results for search `seq` are in your memory"
+// ---------------------------------------------------------------------------------------
+struct PeerFlags {
+    int world, rank;
+    unsigned int* flags[MAX_PEERS];   // flags[p] = rank p's flag array of this parity, [2 * world]
+};
+// Launched after the finalize kernel on the same stream: the kernel boundary makes finalize's
+// stores (local and peer) performed, the system fence orders them before the flag.
+__global__ void exchange_signal_kernel(PeerFlags pf, unsigned int seq, const long long* __restrict__ gstats,
+                                       long long prior_overflow) {
+    const int p = threadIdx.x;
+    if (p >= pf.world) return;
+    unsigned int* f = pf.flags[p] + 2 * pf.rank;
+    const long long ov = gstats[GS_OVERFLOW] + prior_overflow;
+    f[1] = ov > 0x7fffffffll ? 0x7fffffffu : static_cast<unsigned int>(ov);
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // padding for an empty index, and the multi-shard merge
 // ---------------------------------------------------------------------------------------
 __global__ void fill_padding_kernel(float* scores, long long* rows, long long count) {
@@ -739,11 +787,38 @@ __global__ void __launch_bounds__(SEL_THREADS)
 merge_topk_kernel(long long nq, int k, int n_lists, const float* __restrict__ scores,
                   const long long* __restrict__ rows, long long scores_list_stride,
                   long long rows_list_stride, float* __restrict__ out_scores,
-                  long long* __restrict__ out_rows, int P) {
+                  long long* __restrict__ out_rows, int P, const unsigned int* wait_flags,
+                  unsigned int seq, long long* __restrict__ xstatus) {
     extern __shared__ __align__(16) uint8_t msm[];
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(msm);
     const long long q = blockIdx.x;
     const int total = n_lists * k;
+    if (wait_flags) {
+        // peer-direct exchange: list l was stored into this GPU's memory by rank l's finalize
+        // kernel; rank l then published flag word 2l = seq (release, system scope) and its
+        // overflow count in word 2l+1.  Wait for all of them (bounded: a dead peer must not
+        // hang the GPU), then merge as usual.
+        if (threadIdx.x < n_lists) {
+            const unsigned int* f = wait_flags + 2 * threadIdx.x;
+            const long long t0 = clock64();
+            unsigned int v;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (static_cast<int>(v - seq) >= 0) break;
+                if (clock64() - t0 > 8000000000ll) {                  // ~4-6 s
+                    if (xstatus) atomicMax(xstatus, XSTATUS_TIMEOUT);
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        if (xstatus && blockIdx.x == 0 && threadIdx.x == 0) {
+            long long ov = 0;
+            for (int l = 0; l < n_lists; l++) ov += wait_flags[2 * l + 1];
+            atomicMax(xstatus, ov);
+        }
+    }
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         unsigned long long key = 0ull;
         if (i < total) {

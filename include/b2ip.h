@@ -118,6 +118,13 @@ int b2ip_dim(b2ip_handle h);
  * passes the number of rows held by shards 0..g-1). Default 0. */
 int b2ip_set_row_offset(b2ip_handle h, int64_t offset);
 
+/* A shard made of several global row ranges (e.g. every G-th ingest chunk): segment i holds
+ * local rows [local_start[i], local_start[i+1]) = global rows global_start[i] + ...; both
+ * arrays strictly increasing, local_start[0] = 0.  Reported ids are then global without any
+ * post-processing; n_segments = 0 returns to b2ip_set_row_offset's single offset. */
+int b2ip_set_row_segments(b2ip_handle h, int n_segments, const int64_t* local_start,
+                          const int64_t* global_start);
+
 /* replaces scores, indexes = index.search(q, top_docs)         -- src/index.py:42
  * queries [nq,d] fp32; out_scores [nq,k] fp32, per row descending; out_rows [nq,k] int64
  * 0-based insertion-order ids (+ row offset).  Exact ties keep the lower row.  When fewer
@@ -140,6 +147,30 @@ int b2ip_merge_topk(int device, void* cuda_stream, int64_t nq, int k, int n_list
 int b2ip_merge_topk_strided(int device, void* cuda_stream, int64_t nq, int k, int n_lists,
                             const float* scores, const int64_t* rows, int64_t scores_list_stride,
                             int64_t rows_list_stride, float* out_scores, int64_t* out_rows);
+
+/* The same exchange fused behind the search, over peer memory instead of a collective call.
+ * Every rank owns a `gather` buffer of `world` slots ([rows int64 nq*k | scores fp32 nq*k],
+ * slot_bytes apart) and a flag array uint32[2*world], both mapped into every other rank's address
+ * space (CUDA IPC / torch symmetric memory; NVLink P2P).  b2ip_search_exchange runs the local
+ * search with its finalize kernel storing this rank's [nq,k] block straight into slot `rank` of
+ * EVERY rank's gather buffer, publishes flags[p][2*rank] = seq on every rank p, and merges the
+ * world's blocks out of its own gather buffer as soon as all flags are in -- two launches queued
+ * behind the search on the same stream, no host round trip and no separate all-gather.
+ * Callers alternate between two buffer sets (seq parity): a rank can run at most one search
+ * ahead of its slowest peer.  *status = total number of queries, over all ranks, whose candidate
+ * lists overflowed (identical on every rank): when non-zero the merged output is not valid and
+ * every rank must repeat the search through b2ip_search + all-gather + b2ip_merge_topk.
+ * All pointers are device pointers valid on the handle's device; queries [nq,d] fp32. */
+#define B2IP_MAX_PEERS 8
+typedef struct b2ip_exchange_s {
+    int32_t world, rank;
+    int64_t slot_bytes;
+    void* gather[B2IP_MAX_PEERS];   /* gather[p]: rank p's gather buffer of this parity */
+    void* flags[B2IP_MAX_PEERS];    /* flags[p]:  rank p's uint32[2*world] flag array of this parity */
+} b2ip_exchange_t;
+int b2ip_search_exchange(b2ip_handle h, int64_t nq, const float* queries_dev, int k,
+                         const b2ip_exchange_t* ex, uint32_t seq, float* out_scores_dev,
+                         int64_t* out_rows_dev, int64_t* status);
 
 /* replaces faiss.write_index's read of the stored vectors       -- src/index.py:53
  * Copies rows [row0, row0+n) as fp32 into out ([n,d]). */

@@ -19,31 +19,57 @@ n, nq, d = 60_000, 500, 768
 x, q = synth(n, d, 1234), synth(nq, d, 4321)
 x[40_000:40_050] = x[100:150]                       # exact ties that straddle shards
 qd = torch.from_numpy(q).cuda()
+whole = Engine(d, local)
+whole.add(x)
 for k in (10, 100, 1000):
-    idx = ShardedIndex(d, device=local)
-    lo, hi = shard_bounds(n, world, rank)
-    idx.add_local(x[lo:hi], lo)
-    D, I = idx.search(qd, k)
-    if rank == 0:
-        whole = Engine(d, local)
-        whole.add(x)
-        Dw, Iw = whole.search(qd, k)
-        assert torch.equal(I, Iw), f"k={k}: sharded ids differ from single-GPU ids"
-        assert torch.equal(D, Dw), f"k={k}: sharded scores differ"
-    # round-robin chunk ingest (multi-segment id mapping) gives the same answer too
-    idx2 = ShardedIndex(d, device=local)
-    for a in range(0, n, 7000):
-        idx2.add_replicated(x[a:a + 7000])
-    D2, I2 = idx2.search(qd, k)
-    assert torch.equal(I2, I) and torch.equal(D2, D), f"k={k}: replicated ingest differs"
+    Dw, Iw = whole.search(qd, k)
+    for peer in (True, False):          # fused peer-direct exchange / NCCL all-gather + merge
+        idx = ShardedIndex(d, device=local, peer_exchange=peer)
+        lo, hi = shard_bounds(n, world, rank)
+        idx.add_local(x[lo:hi], lo)
+        D, I = idx.search(qd, k)
+        assert torch.equal(I, Iw), f"k={k} peer={peer}: sharded ids differ from single-GPU ids"
+        assert torch.equal(D, Dw), f"k={k} peer={peer}: sharded scores differ"
+        assert idx.exchange_searches == (1 if peer else 0)
+        # round-robin chunk ingest (several row segments per shard) gives the same answer too
+        idx2 = ShardedIndex(d, device=local, peer_exchange=peer)
+        for a in range(0, n, 7000):
+            idx2.add_replicated(x[a:a + 7000])
+        D2, I2 = idx2.search(qd, k)
+        assert torch.equal(I2, Iw) and torch.equal(D2, Dw), f"k={k} peer={peer}: replicated ingest differs"
+
+# peer-direct exchange over many searches: both parities, buffers regrown, batch sizes of the
+# latency regime, and a rank with an EMPTY shard
+idx = ShardedIndex(d, device=local)
+idx3 = ShardedIndex(d, device=local)
+lo, hi = shard_bounds(n, world, rank)
+idx.add_local(x[lo:hi], lo)
+if rank == 0:
+    idx3.add_local(x, 0)                # every row on rank 0, nothing anywhere else
+for it, nqs in enumerate([1, 7, 64, 64, 500, 3, 128, 129, 500, 1]):
+    Dw, Iw = whole.search(qd[:nqs].contiguous(), 10)
+    for index in (idx, idx3):
+        D, I = index.search(qd[:nqs].contiguous(), 10)
+        assert torch.equal(I, Iw) and torch.equal(D, Dw), f"exchange search {it} (nq={nqs}) differs"
+assert idx.exchange_searches == 10 and idx3.exchange_searches == 10
+
+# adversarial corpus (ascending scores): candidate lists overflow on the rank that holds the tail;
+# every rank sees the same non-zero status and repeats the search through the all-gather path
+u = synth(1, 128, 3)[0]
+xa = (u[None, :] * (1.0 + np.arange(60_000, dtype=np.float32)[:, None] * 1e-5)).astype(np.float32)
+qa = torch.from_numpy(np.tile(u[None, :], (8, 1)) * np.linspace(0.5, 1.5, 8, dtype=np.float32)[:, None]).cuda()
+ia = ShardedIndex(128, device=local)
+lo, hi = shard_bounds(60_000, world, rank)
+ia.add_local(xa[lo:hi], lo)
+Da, Ia = ia.search(qa, 100)
+assert ia.exchange_searches == 0, "overflow must send every rank to the all-gather path"
+assert torch.equal(Ia[0].cpu(), torch.arange(59_999, 59_899, -1)), Ia[0][:5]
 if rank == 0:
     # the single-process driver of the same shards (b2ip.multi): one engine per visible GPU
     from b2ip import MultiGpuEngine
     m = MultiGpuEngine(d)
     assert len(m.engines) >= world
     m.add(x[:25_000]); m.add(x[25_000:])
-    whole = Engine(d, local)
-    whole.add(x)
     for k in (10, 100):
         Dw, Iw = whole.search(q, k)
         Dm, Im = m.search(q, k)
