@@ -298,7 +298,8 @@ def main():
 
     # ---------------------------------------------------------------- device-resident timing
     agg = {"coarse_ms": 0.0, "coarse_flops": 0.0, "coarse_launches": 0, "launches": 0,
-           "candidates": 0, "rescored": 0, "fallback": 0, "slabs": 0}
+           "candidates": 0, "rescored": 0, "fallback": 0, "slabs": 0, "refresh_ms": 0.0,
+           "finalize_ms": 0.0, "device_ms": 0.0}
 
     def step_device():
         D, I = index.search(q_dev, k)
@@ -308,6 +309,8 @@ def main():
         agg["launches"] += st["total_launches"] + (1 if world > 1 else 0)
         agg["candidates"] += st["candidates"]; agg["rescored"] += st["rescored"]
         agg["fallback"] += st["fallback_queries"]; agg["slabs"] += st["slabs"]
+        agg["refresh_ms"] += st["refresh_ms"]; agg["finalize_ms"] += st["finalize_ms"]
+        agg["device_ms"] += st["total_ms"]
         return D, I
 
     for _ in range(args.warmup):
@@ -429,7 +432,13 @@ def main():
             "detail": {"ingest_s": t_ing, "rows_per_gpu": hi - lo,
                        "candidates_per_query_per_step": agg["candidates"] / max(1, args.steps) / nq,
                        "rescored_per_query_per_step": agg["rescored"] / max(1, args.steps) / nq,
-                       "fallback_queries": agg["fallback"], "slabs_per_step": agg["slabs"] / max(1, args.steps)},
+                       "fallback_queries": agg["fallback"], "slabs_per_step": agg["slabs"] / max(1, args.steps),
+                       "rank0_ms_per_step": {"coarse": agg["coarse_ms"] / max(1, args.steps),
+                                             "refresh": agg["refresh_ms"] / max(1, args.steps),
+                                             "finalize": agg["finalize_ms"] / max(1, args.steps),
+                                             "search_device_total": agg["device_ms"] / max(1, args.steps)},
+                       "exchange": ("peer-direct (b2ip_search_exchange)" if getattr(index, "exchange_searches", 0) > 0
+                                    else ("nccl all-gather + merge" if world > 1 else "none"))},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -139,6 +139,8 @@ class ShardedIndex:
                 return D, I
             # some rank overflowed a candidate list (same status everywhere): all ranks repeat
             # the search below, where the exact fallback runs before the exchange
+        if os.environ.get("B2IP_X_PROBE") == "1" and self._x_ex is None and self._engine_writes_in_place():
+            self._exchange_buffers(int(queries.shape[0]), int(k))   # experiment: map, never use
         return self._search_allgather(queries, k, mode)
 
     # -- peer-direct exchange --------------------------------------------------------

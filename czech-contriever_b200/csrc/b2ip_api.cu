@@ -36,6 +36,7 @@ using namespace b2ip;
 #define B2IP_DEFAULT_SHADOW SH_BF16
 #endif
 static constexpr int SH_DEFAULT_F32_STORE = B2IP_DEFAULT_SHADOW;
+static constexpr int MAX_SMEM_OPTIN = 227 * 1024;     // dynamic shared memory a CTA may opt in to (sm_100)
 
 namespace {
 
@@ -84,6 +85,7 @@ struct b2ip_index_s {
     int dbg = 0;
     int verbose = 0;
     int pair = 1;                         // CTA-pair (cta_group::2) scoring kernel when nq > 128
+    int stream_kernel = 1;                // nq <= 64: streaming kernel (corpus on the MMA's M side)
     int dense_first = 1;                  // first slab stored positionally (no counters / hit extraction)
     int fuse_refresh = 1;                 // last threshold refresh inside the finalize kernel
     long long cand_budget_bytes = 6ll << 30;
@@ -492,6 +494,16 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         CUtensorMap tmap_q;
         RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, TILE_Q));
         const bool use_pair = h->pair && nqb > TILE_Q && h->sm_count >= 2;
+        // small batches: streaming kernel (corpus tile on the M side, resident queries) when the
+        // padded batch fits next to at least 4 corpus stages in shared memory
+        const int nq_s = nqb <= 32 ? 32 : 64;
+        const size_t q_bytes = static_cast<size_t>(h->d_pad / KBLOCK_ELEMS) * nq_s * KBLOCK_BYTES;
+        const int stream_stages = static_cast<int>(std::min<long long>(
+            STREAM_MAX_STAGES,
+            (static_cast<long long>(MAX_SMEM_OPTIN) - STREAM_MISC_BYTES - static_cast<long long>(q_bytes)) / STREAM_X_STAGE_BYTES));
+        const bool use_stream = h->stream_kernel && nqb <= 64 && stream_stages >= 4;
+        const size_t stream_smem = static_cast<size_t>(std::max(stream_stages, 0)) * STREAM_X_STAGE_BYTES + q_bytes + STREAM_MISC_BYTES;
+        if (use_stream) RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, nq_s));
 
         CoarseParams cp{};
         cp.num_k_blocks = h->d_pad / KBLOCK_ELEMS;
@@ -508,6 +520,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         cp.hint_x = hint_policy(h->hint_x);
         cp.dbg = h->dbg;
         cp.idesc = use_pair ? IDESC_PAIR[h->sh] : IDESC_SINGLE[h->sh];
+        if (use_stream) cp.idesc = ptx::umma_idesc(h->sh == SH_F16 ? 0 : 1, STREAM_TILE_X, nq_s);
 
         int64_t done = 0;
         long long overflowed = 0;
@@ -528,13 +541,22 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             s = std::min<int64_t>(s, n - done);
             cp.x_row0 = done;
             cp.x_row_end = done + s;
-            cp.x_tiles = static_cast<int>((s + TILE_X - 1) / TILE_X);
+            cp.x_tiles = use_stream ? static_cast<int>((s + STREAM_TILE_X - 1) / STREAM_TILE_X)
+                                    : static_cast<int>((s + TILE_X - 1) / TILE_X);
             cp.dense = (done == 0 && dense_first) ? 1 : 0;
             const bool last = done + s >= n;
             const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
             cudaEvent_t e0 = get_event(h, ev_used++), e1 = get_event(h, ev_used++);
             CU_TRY(h, cudaEventRecord(e0, h->stream));
-            if (use_pair) {
+            if (use_stream) {
+                const int grid = static_cast<int>(std::min<long long>(cp.x_tiles, h->sm_count));
+                if (nq_s == 32)
+                    coarse_stream_kernel<32><<<grid, COARSE_THREADS, stream_smem, h->stream>>>(
+                        tmap_q, tmap_x_pair, cp, stream_stages);
+                else
+                    coarse_stream_kernel<64><<<grid, COARSE_THREADS, stream_smem, h->stream>>>(
+                        tmap_q, tmap_x_pair, cp, stream_stages);
+            } else if (use_pair) {
                 const int grid = 2 * static_cast<int>(std::min<long long>(tiles, h->sm_count / 2));
                 coarse_filter_pair_kernel<<<grid, COARSE_THREADS, PAIR_SMEM_BYTES, h->stream>>>(
                     tmap_q, tmap_x_pair, cp);
@@ -791,6 +813,8 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
         if (cudaFuncSetAttribute(coarse_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(coarse_stream_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
+            cudaFuncSetAttribute(coarse_stream_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
             cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
             cudaFuncSetAttribute(finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
             cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -800,6 +824,7 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     h->gx = std::max(1, h->sm_count / 2);   // = clusters of the pair kernel: one query tile per wave,
                                             // the corpus tiles of a group stay L2 resident (measured best)
     if (const char* s = getenv("B2IP_GX")) h->gx = std::max(1, atoi(s));
+    if (const char* s = getenv("B2IP_STREAM_KERNEL")) h->stream_kernel = atoi(s);
     if (const char* s = getenv("B2IP_HINT_Q")) h->hint_q = atoi(s);
     if (const char* s = getenv("B2IP_HINT_X")) h->hint_x = atoi(s);
     if (const char* s = getenv("B2IP_CAND_BUDGET_MB")) h->cand_budget_bytes = std::max(1ll, atoll(s)) << 20;
@@ -850,6 +875,7 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "verbose") h->verbose = static_cast<int>(value);
     else if (n == "pair") h->pair = static_cast<int>(value);
     else if (n == "dense_first") h->dense_first = static_cast<int>(value);
+    else if (n == "stream_kernel") h->stream_kernel = static_cast<int>(value);
     else if (n == "fuse_refresh") h->fuse_refresh = static_cast<int>(value);
     else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;
     else if (n == "shadow_f16") {

@@ -494,4 +494,185 @@ coarse_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
 }
 
+// =======================================================================================
+// Streaming variant for small query batches (nq <= 64): BASELINE config 5, the HBM-bound
+// latency regime.  Operands are swapped with respect to the kernels above: the CORPUS tile is
+// the M side of the MMA (128 rows = 128 TMEM lanes) and the padded query batch the N side
+// (NQ = 32 or 64 columns), so a tile costs 128 x NQ x d MACs instead of 128 x 256 x d for 256
+// rows -- 2-4x less tensor-core work (and power: this regime is power-capped too) for the same
+// bytes.  The whole query batch stays RESIDENT in shared memory (loaded once per CTA), so the
+// only L2->SM stream is the corpus itself: STAGES x 16 KiB of TMA loads in flight per SM.
+//   warp 0 / lane 0 : TMA producer (queries once, then 128-row corpus tiles, k-block by k-block)
+//   warp 1 / lane 0 : MMA issuer   (4 x tcgen05.mma 128 x NQ x 16 per k-block)
+//   warp 2          : TMEM allocator (4 accumulator stages of NQ columns)
+//   warps 4..7      : filter epilogue; thread = corpus row, its NQ scores against the NQ
+//                     per-query thresholds held in registers
+// =======================================================================================
+constexpr int STREAM_TILE_X = 128;
+constexpr int STREAM_MAX_STAGES = 8;
+constexpr int STREAM_ACC = 4;
+constexpr int STREAM_X_STAGE_BYTES = STREAM_TILE_X * KBLOCK_BYTES;   // 16 KiB
+constexpr int STREAM_MISC_BYTES = 1024 /*align*/ + 256 /*barriers*/;
+
+template <int NQ>
+__global__ void __launch_bounds__(COARSE_THREADS, 1)
+coarse_stream_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                     const __grid_constant__ CUtensorMap tmap_x, const CoarseParams p,
+                     const int stages) {
+    static_assert(NQ == 32 || NQ == 64, "query batch is padded to 32 or 64 columns");
+    constexpr uint32_t kTmemCols = STREAM_ACC * NQ;                  // 128 or 256: powers of two
+    constexpr int Q_KB_BYTES = NQ * KBLOCK_BYTES;                     // one k-block of the batch
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_x = smem;                                           // [stages][128 x 128 B]
+    uint8_t* smem_q = smem + stages * STREAM_X_STAGE_BYTES;           // [num_k_blocks][NQ x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_q + p.num_k_blocks * Q_KB_BYTES);
+    uint64_t* full_bar = bars;                                        // [STREAM_MAX_STAGES]
+    uint64_t* empty_bar = bars + STREAM_MAX_STAGES;                   // [STREAM_MAX_STAGES]
+    uint64_t* tfull_bar = bars + 2 * STREAM_MAX_STAGES;               // [STREAM_ACC]
+    uint64_t* tempty_bar = bars + 2 * STREAM_MAX_STAGES + STREAM_ACC; // [STREAM_ACC]
+    uint64_t* qfull_bar = bars + 2 * STREAM_MAX_STAGES + 2 * STREAM_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.x_tiles;                                // tiles of 128 corpus rows
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_q);
+        ptx::prefetch_tmap(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STREAM_MAX_STAGES; s++) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < STREAM_ACC; s++) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 128);
+        }
+        ptx::mbar_init(qfull_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            ptx::mbar_expect_tx(qfull_bar, static_cast<uint32_t>(p.num_k_blocks * Q_KB_BYTES));
+            for (int kb = 0; kb < p.num_k_blocks; kb++)
+                ptx::tma_load_2d(smem_q + kb * Q_KB_BYTES, &tmap_q, qfull_bar, kb * KBLOCK_ELEMS, 0,
+                                 p.hint_q);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const long long x_row = p.x_row0 + static_cast<long long>(t) * STREAM_TILE_X;
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&full_bar[stage], STREAM_X_STAGE_BYTES);
+                    ptx::tma_load_2d(smem_x + stage * STREAM_X_STAGE_BYTES, &tmap_x, &full_bar[stage],
+                                     kb * KBLOCK_ELEMS, static_cast<int32_t>(x_row), p.hint_x);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            ptx::mbar_wait(qfull_bar, 0);
+            ptx::tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * NQ);
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem_x + stage * STREAM_X_STAGE_BYTES);
+                    const uint32_t b_addr = ptx::smem_u32(smem_q + kb * Q_KB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < KBLOCK_BYTES / UMMA_K_BYTES; k++) {
+                        const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr + k * UMMA_K_BYTES);
+                        const uint64_t bdesc = ptx::umma_desc_k_sw128(b_addr + k * UMMA_K_BYTES);
+                        ptx::mma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (kb | k) != 0);
+                    }
+                    ptx::tc_commit(&empty_bar[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::tc_commit(&tfull_bar[as]);
+                if (++as == STREAM_ACC) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== filter epilogue: thread = corpus row =====================
+        const int wq = warp & 3;
+        float thr_r[NQ];
+#pragma unroll
+        for (int j = 0; j < NQ; j++)
+            thr_r[j] = j < p.nq ? __ldg(p.thr + j) : __int_as_float(0x7f800000);   // +inf: padding
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const long long row = p.x_row0 + static_cast<long long>(t) * STREAM_TILE_X + wq * 32 + lane;
+            const bool row_ok = row < p.x_row_end;
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * NQ);
+#pragma unroll
+            for (int c = 0; c < NQ / 32; c++) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(taddr + c * 32, v);
+                ptx::tmem_ld_wait();
+                if (p.dense) {
+                    // first slab: list position = row offset in the slab; for a fixed query the 32
+                    // lanes of a warp store 32 consecutive keys
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (c * 32 + j < p.nq)
+                                p.cand[static_cast<long long>(c * 32 + j) * p.cap + (row - p.x_row0)] =
+                                    make_key(__uint_as_float(v[j]), static_cast<uint32_t>(row));
+                    }
+                } else {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        mask |= (__uint_as_float(v[j]) > thr_r[c * 32 + j]) ? (1u << j) : 0u;
+                    if (!row_ok) mask = 0;
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int q = c * 32 + j;
+                        const uint32_t bits = select32(v, j);
+                        const int slot = atomicAdd(p.cnt + q, 1);
+                        if (slot < p.cap)
+                            p.cand[static_cast<long long>(q) * p.cap + slot] =
+                                make_key(__uint_as_float(bits), static_cast<uint32_t>(row));
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[as]);
+            if (++as == STREAM_ACC) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
 }  // namespace b2ip
