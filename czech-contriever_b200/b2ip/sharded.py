@@ -131,7 +131,13 @@ class ShardedIndex:
         if self.world == 1:
             return self.search_local(queries, k, mode)
         if self.peer_exchange and mode != "exact" and int(queries.shape[0]) > 0:
-            ex = self._exchange_buffers(int(queries.shape[0]), int(k))
+            try:
+                ex = self._exchange_buffers(int(queries.shape[0]), int(k))
+            except Exception as e:  # noqa: BLE001 - no symmetric memory on this box (same on every rank)
+                import warnings
+                warnings.warn(f"peer-direct exchange unavailable ({e!r}); using the NCCL all-gather path")
+                self.peer_exchange = False
+                return self._search_allgather(queries, k, mode)
             self._x_seq += 1
             D, I, status = self.engine.search_exchange(queries, k, ex[self._x_seq & 1], self._x_seq)
             if status == 0:
@@ -139,8 +145,6 @@ class ShardedIndex:
                 return D, I
             # some rank overflowed a candidate list (same status everywhere): all ranks repeat
             # the search below, where the exact fallback runs before the exchange
-        if os.environ.get("B2IP_X_PROBE") == "1" and self._x_ex is None and self._engine_writes_in_place():
-            self._exchange_buffers(int(queries.shape[0]), int(k))   # experiment: map, never use
         return self._search_allgather(queries, k, mode)
 
     # -- peer-direct exchange --------------------------------------------------------
