@@ -558,3 +558,16 @@ def test_non_finite_values_follow_faiss(fo, store, shadow):
     st = e2.stats()
     # the non-finite rows did not push everything onto the exact path
     assert st["fallback_queries"] <= 1, st
+
+
+@pytest.mark.parametrize("d,nq", [(2048, 8), (1024, 40), (1024, 20), (64, 64)])
+def test_small_batches_across_dimensions(fo, d, nq):
+    """Batches <= 64 take the streaming kernel (queries resident in shared memory) when the padded
+    batch fits next to >= 4 corpus stages, the single-CTA kernel otherwise (d = 2048 here)."""
+    x = synth(30_000, d, 141)
+    q = synth(nq, d, 142)
+    e = _engine(x)
+    D, I = e.search(q, 10)
+    assert e.stats()["fallback_queries"] == 0 and e.stats()["slabs"] >= 2
+    Do, Io = fo.search(q, x, 10)
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
