@@ -306,7 +306,9 @@ def main():
         st = index.engine.stats()
         agg["coarse_ms"] += st["coarse_ms"]; agg["coarse_flops"] += st["coarse_flops"]
         agg["coarse_launches"] += st["coarse_launches"]
-        agg["launches"] += st["total_launches"] + (1 if world > 1 else 0)
+        # all-gather path: + the NCCL kernel and the merge kernel; the peer-direct exchange's two
+        # launches (signal, waiting merge) are already in the library's count
+        agg["launches"] += st["total_launches"] + (2 if world > 1 and getattr(index, "exchange_searches", 0) == 0 else 0)
         agg["candidates"] += st["candidates"]; agg["rescored"] += st["rescored"]
         agg["fallback"] += st["fallback_queries"]; agg["slabs"] += st["slabs"]
         agg["refresh_ms"] += st["refresh_ms"]; agg["finalize_ms"] += st["finalize_ms"]
@@ -395,10 +397,19 @@ def main():
         bytes_rank = (hi - lo) * d * 2.0 * args.steps
         gbs = bytes_rank / (agg["coarse_ms"] / 1e3) / 1e9 if agg["coarse_ms"] > 0 else 0.0
         gbs = -max_over_ranks(-gbs)
+        try:   # dram bytes of the streaming kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r1c_stream_ncu.json")) as f:
+                prof = json.load(f)
+            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+            traffic_note = (f"ncu capture of one launch ({prof['launch']}, {prof['algorithmic_bytes']:.4e} "
+                            f"algorithmic bytes, {prof['duration_ms']:.3f} ms): dram read+write bytes; {prof['source']}")
+        except Exception:
+            pass
         roofline = {
             "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-            "traffic": None,
-            "kernel": "coarse_filter_kernel<false> (TMA-streamed 16-bit corpus tiles, tcgen05 scoring, fused filter)",
+            "traffic": traffic, "traffic_note": traffic_note,
+            "kernel": ("coarse_stream_kernel (corpus tile on the MMA's M side, resident queries, TMA-streamed 16-bit rows)"
+                       if nq <= 64 else "coarse_filter_kernel<false> (TMA-streamed 16-bit corpus tiles, fused filter)"),
             "peak_source": peak_src + " hbm_gbs (copy bandwidth)",
             "bytes_per_launch_avg": bytes_rank / max(1, agg["coarse_launches"]),
             "launches": agg["coarse_launches"], "kernel_ms_per_step": coarse_ms / args.steps,

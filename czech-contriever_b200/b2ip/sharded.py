@@ -157,9 +157,8 @@ class ShardedIndex:
         from ._lib import Exchange
         torch, dist = self._torch, self._dist
         dev = torch.device("cuda", self.engine.device)
-        slot = 1 << 12
-        while slot < need:
-            slot <<= 1
+        # 25 % headroom (fewer collective re-allocations as nq*k creeps up), 64 KiB granules
+        slot = max(1 << 16, (need + need // 4 + 65535) // 65536 * 65536)
         total = 2 * self.world * slot + 2 * self.FLAG_BYTES
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)                 # nobody still uses the old buffers
