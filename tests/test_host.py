@@ -337,3 +337,82 @@ def test_segment_map_local_to_global(built):
     assert list(m.overlaps(419, 2000)) == [(79, 419, 1), (80, 1000, 5)]
     with pytest.raises(ValueError):
         m.append(900, 1)
+
+
+class _OracleBackedEngine:
+    """CPU stand-in for b2ip.Engine in the Indexer host-logic test (tests only): keeps the rows
+    in the storage type it was created with and answers searches with the oracle."""
+    created = []
+
+    def __init__(self, d, device=0, store="f32", shadow=None):
+        self.d, self.device, self.store = d, device, store
+        self.rows = np.empty((0, d), np.float32)
+        _OracleBackedEngine.created.append(store)
+
+    def reserve(self, n): pass
+    def close(self): pass
+
+    @property
+    def ntotal(self): return self.rows.shape[0]
+
+    def add(self, rows):
+        rows = np.asarray(rows)
+        if self.store == "f16":
+            rows = rows.astype(np.float16)
+        self.rows = np.concatenate([self.rows, rows.astype(np.float32)])
+
+    def export_rows(self, r0, n): return self.rows[r0:r0 + n].copy()
+
+    def search(self, q, k, mode="auto", out=None):
+        from oracle import flatip_oracle as fo
+        return fo.search(np.asarray(q, np.float32), self.rows, k)
+
+
+def test_indexer_host_logic_with_a_stand_in_engine(tmp_path, built, monkeypatch):
+    """The drop-in Indexer above the C ABI, on CPU: same calls as the reference restatement
+    (oracle.OracleIndexer <- reference src/index.py:15-73) give the same ids, scores, files and
+    the reference's `index_id_to_db_id[-1]` quirk; float16 chunks select the lossless fp16 store and
+    a later fp32 chunk migrates the rows to fp32 master storage."""
+    from oracle import flatip_oracle as fo
+    from helpers import synth
+    import b2ip.indexer as bi
+    monkeypatch.setattr(bi, "Engine", _OracleBackedEngine)
+    _OracleBackedEngine.created.clear()
+    d = 32
+    a = (synth(300, d, 1, normalize=False)).astype(np.float16)
+    b = (synth(200, d, 2, normalize=False)).astype(np.float16)
+    c = synth(100, d, 3, normalize=False)                       # fp32, not fp16-valued
+    ours, ref = bi.Indexer(d, 0, 8, device=0), fo.OracleIndexer(d, 0, 8)
+    for idx in (ours, ref):
+        idx.index_data([f"p{i}" for i in range(300)], a)
+        idx.index_data([f"p{300 + i}" for i in range(200)], b)
+    assert ours.index.store == "f16" and _OracleBackedEngine.created == ["f32", "f16"]
+    q = synth(7, d, 4, normalize=False).astype(np.float16)
+    for (gi, gs), (wi, ws) in zip(ours.search_knn(q, 10), ref.search_knn(q, 10)):
+        assert gi == wi and isinstance(gi[0], str) and np.array_equal(gs, ws) and gs.dtype == np.float32
+    for idx in (ours, ref):
+        idx.index_data([f"p{500 + i}" for i in range(100)], c)
+    assert ours.index.store == "f32" and ours.index.ntotal == 600          # migrated, nothing lost
+    assert np.array_equal(ours.index.rows, ref.rows)
+    got, want = ours.search_knn(q, 10), ref.search_knn(q, 10)
+    for (gi, gs), (wi, ws) in zip(got, want):
+        assert gi == wi and np.array_equal(gs, ws)
+    # persistence: byte-identical index.faiss, same meta, and a reload answers the same
+    da, db = tmp_path / "a", tmp_path / "b"
+    da.mkdir(); db.mkdir()
+    ours.serialize(str(da)); ref.serialize(str(db))
+    assert (da / "index.faiss").read_bytes() == (db / "index.faiss").read_bytes()
+    assert (da / "index_meta.faiss").read_bytes() == (db / "index_meta.faiss").read_bytes()
+    again = bi.Indexer(d, 0, 8, device=0)
+    again.deserialize_from(str(db))
+    for (gi, gs), (wi, ws) in zip(again.search_knn(q, 10), want):
+        assert gi == wi and np.array_equal(gs, ws)
+    # fewer rows than k: faiss pads with -1 and the reference maps -1 to the LAST id (src/index.py:44)
+    small, small_ref = bi.Indexer(d, 0, 8, device=0), fo.OracleIndexer(d, 0, 8)
+    for idx in (small, small_ref):
+        idx.index_data(["x", "y", "z"], c[:3])
+    (gi, gs), (wi, ws) = small.search_knn(q[:1], 5)[0], small_ref.search_knn(q[:1], 5)[0]
+    assert gi == wi and gi[3:] == ["z", "z"] and np.array_equal(gs, ws)
+    assert small.search_knn(np.zeros((0, d), np.float32), 5) == []
+    with pytest.raises(NotImplementedError):
+        bi.Indexer(d, 8, 8)
