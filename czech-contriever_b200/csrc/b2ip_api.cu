@@ -378,7 +378,7 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
     CU_TRY(h, cudaMemcpyAsync(qlist_dev, qlist_host, static_cast<size_t>(nql) * sizeof(int),
                               cudaMemcpyHostToDevice, h->stream));
     const size_t sq_bytes = static_cast<size_t>(EXACT_QB) * h->d * sizeof(float);
-    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
+    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(double);
     const int sgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
     const int hgrid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(h->sm_count) * 4));
     for (int64_t g0 = 0; g0 < nql; g0 += EXACT_QB) {
@@ -445,7 +445,10 @@ int enqueue_exchange(b2ip_handle h, int64_t nq, int k) {
 int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_scores,
                   int64_t* d_rows) {
     const int64_t n = h->n;
-    const int cap = std::max(4096, 16 * k);
+    // List capacity: lists of <= 4096 keys are refreshed / finalized entirely in shared memory
+    // (REFRESH_SMEM_KEYS, SORT_CAP), so k <= 1024 keeps that size and pays with a few more slabs
+    // (measured at k = 1000: refresh + finalize 12 % of the step with 16k-key lists selected out of L2)
+    const int cap = std::max(4096, 4 * k);
     int64_t qb_max = h->cand_budget_bytes / (static_cast<int64_t>(cap) * 8);
     qb_max = std::max<int64_t>(TILE_Q, qb_max / TILE_Q * TILE_Q);
     const int64_t qb = std::min<int64_t>(nq, qb_max);
@@ -460,7 +463,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
     RC_TRY(ensure(h, h->flags, qb * sizeof(int)));
     RC_TRY(ensure(h, h->cand, static_cast<size_t>(qb) * cap * 8));
 
-    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
+    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(double);
     // tensor maps of the corpus are rebuilt only when the rows moved or grew
     if (h->tmap_x_base != h->x16 || h->tmap_x_rows != n) {
         RC_TRY(make_tmap_bf16(h, &h->tmap_x_pair, h->x16, n, h->d_pad, 128));
@@ -809,7 +812,7 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     {   // opt-in shared memory sizes, once per process and device
         // (upper bounds for the largest supported d, so handles of different d can coexist)
-        const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(B2IP_MAX_D) * sizeof(float);
+        const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(B2IP_MAX_D) * sizeof(double);
         if (cudaFuncSetAttribute(coarse_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES) != cudaSuccess ||

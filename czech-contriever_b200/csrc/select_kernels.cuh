@@ -510,7 +510,9 @@ template <bool kRescore>
 __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizeParams p) {
     extern __shared__ __align__(16) uint8_t fsm[];
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(fsm);   // [SORT_CAP]
-    float* sq = reinterpret_cast<float*>(fsm + SORT_CAP * sizeof(unsigned long long));  // [d]
+    // the query, widened to fp64 ONCE: the rescore is bound by F2F.F64.F32 conversions (16 per
+    // clock per SM), so converting q per row would double its cost
+    double* sq = reinterpret_cast<double*>(fsm + SORT_CAP * sizeof(unsigned long long));  // [d]
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_krem;
@@ -535,9 +537,9 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
 
     if (kRescore) {
         for (int j = threadIdx.x; j < p.d; j += blockDim.x)
-            sq[j] = p.q32[static_cast<long long>(q) * p.d + j];
+            sq[j] = static_cast<double>(p.q32[static_cast<long long>(q) * p.d + j]);
         __syncthreads();
-        const float4* q4 = reinterpret_cast<const float4*>(sq);
+        const double2* q2 = reinterpret_cast<const double2*>(sq);
         // two candidates per warp iteration: both rows' loads are in flight before either
         // reduction starts (the gather is latency-bound: 3 KB from a random HBM page per row)
         for (int i = warp; i < n; i += 2 * nw) {
@@ -549,15 +551,15 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
             for (int j = lane; j < p.d / 4; j += 32) {
                 const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j, p.sh);
                 const float4 a2 = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j, p.sh);
-                const float4 b = q4[j];
-                acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
-                acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
-                acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
-                acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
-                acc2 = fma(static_cast<double>(a2.x), static_cast<double>(b.x), acc2);
-                acc2 = fma(static_cast<double>(a2.y), static_cast<double>(b.y), acc2);
-                acc2 = fma(static_cast<double>(a2.z), static_cast<double>(b.z), acc2);
-                acc2 = fma(static_cast<double>(a2.w), static_cast<double>(b.w), acc2);
+                const double2 b01 = q2[2 * j], b23 = q2[2 * j + 1];
+                acc = fma(static_cast<double>(a.x), b01.x, acc);
+                acc = fma(static_cast<double>(a.y), b01.y, acc);
+                acc = fma(static_cast<double>(a.z), b23.x, acc);
+                acc = fma(static_cast<double>(a.w), b23.y, acc);
+                acc2 = fma(static_cast<double>(a2.x), b01.x, acc2);
+                acc2 = fma(static_cast<double>(a2.y), b01.y, acc2);
+                acc2 = fma(static_cast<double>(a2.z), b23.x, acc2);
+                acc2 = fma(static_cast<double>(a2.w), b23.y, acc2);
             }
             acc = warp_sum(acc);
             acc2 = warp_sum(acc2);
