@@ -88,6 +88,7 @@ struct b2ip_index_s {
     int stream_kernel = 1;                // nq <= 64: streaming kernel (corpus on the MMA's M side)
     int dense_first = 1;                  // first slab stored positionally (no counters / hit extraction)
     int fuse_refresh = 1;                 // last threshold refresh inside the finalize kernel
+    int two_stage = 1;                    // finalize rescoring in two stages (window eps instead of 2 eps)
     long long cand_budget_bytes = 6ll << 30;
     CUtensorMap tmap_x, tmap_x_pair;      // cached TMA descriptors of x16 (single / pair box)
     // peer-direct exchange of the current b2ip_search_exchange call (n_extra == 0 otherwise)
@@ -625,6 +626,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         fp.out_scores = d_scores + q0 * k;
         fp.out_rows = reinterpret_cast<long long*>(d_rows) + q0 * k;
         fp.gstats = h->gstats;
+        fp.eps2 = h->two_stage ? reinterpret_cast<const float*>(h->eps2.p) : nullptr;
         fp.n_extra = h->n_extra;
         for (int e = 0; e < h->n_extra; e++) {
             fp.extra_r[e] = reinterpret_cast<long long*>(h->extra_base[e]) + q0 * k;
@@ -880,6 +882,7 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "dense_first") h->dense_first = static_cast<int>(value);
     else if (n == "stream_kernel") h->stream_kernel = static_cast<int>(value);
     else if (n == "fuse_refresh") h->fuse_refresh = static_cast<int>(value);
+    else if (n == "two_stage") h->two_stage = static_cast<int>(value);
     else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;
     else if (n == "shadow_f16") {
         // operand type of the coarse pass of an fp32-stored index; only before the first row

@@ -344,7 +344,7 @@ __device__ int block_compact(const unsigned long long* keys, int n, bool by_key,
 // counting pass, one block barrier, one writing pass (2 barriers instead of 2 per 256 keys).
 __device__ int block_compact_disjoint(const unsigned long long* keys, int n, bool by_key,
                                       uint32_t hi_thr, unsigned long long key_thr,
-                                      unsigned long long* out, int* s_warp) {
+                                      unsigned long long* out, int* s_warp, bool invert = false) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int seg = ((n + nw - 1) / nw + 31) & ~31;
     const int b = warp * seg, e = min(n, b + seg);
@@ -355,6 +355,7 @@ __device__ int block_compact_disjoint(const unsigned long long* keys, int n, boo
         if (i < e) {
             const unsigned long long key = keys[i];
             keep = by_key ? (key >= key_thr) : (static_cast<uint32_t>(key >> 32) > hi_thr);
+            keep = keep != invert;
         }
         mine += __popc(__ballot_sync(0xffffffffu, keep));
     }
@@ -373,6 +374,7 @@ __device__ int block_compact_disjoint(const unsigned long long* keys, int n, boo
         if (i < e) {
             key = keys[i];
             keep = by_key ? (key >= key_thr) : (static_cast<uint32_t>(key >> 32) > hi_thr);
+            keep = keep != invert;
         }
         const unsigned int ballot = __ballot_sync(0xffffffffu, keep);
         if (keep) out[off + __popc(ballot & ((1u << lane) - 1u))] = key;
@@ -472,6 +474,7 @@ struct FinalizeParams {
     // fused last threshold refresh (tensor path; nullptr otherwise): the raw fill counters, the
     // kept counts, thresholds, bounds and flags the refresh kernel would have updated
     int* r_cnt; int* r_kept; float* r_thr; const float* r_eps2; int* r_flags;
+    const float* eps2;                // [slots] 2*eps per query: enables the two-stage rescore
     const float* q32;                 // [*, d] fp32 queries (rescore)
     const float* x32;                 // [n, d] fp32 corpus (rescore), or nullptr:
     const __nv_bfloat16* x16;         // [n, d_pad] 16-bit corpus when the index stores bf16 / fp16
@@ -517,6 +520,7 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
     __shared__ unsigned long long s_prefix;
     __shared__ int s_krem;
     __shared__ int s_warp[SEL_THREADS / 32];
+    __shared__ unsigned int s_min;
 
     const int slot = blockIdx.x;
     if (p.flags && (p.flags[slot] & FLAG_OVERFLOW)) return;
@@ -540,38 +544,75 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
             sq[j] = static_cast<double>(p.q32[static_cast<long long>(q) * p.d + j]);
         __syncthreads();
         const double2* q2 = reinterpret_cast<const double2*>(sq);
-        // two candidates per warp iteration: both rows' loads are in flight before either
-        // reduction starts (the gather is latency-bound: 3 KB from a random HBM page per row)
-        for (int i = warp; i < n; i += 2 * nw) {
-            const int i2 = i + nw;
-            const bool has2 = i2 < n;
-            const uint32_t row = key_row(keys[i]);
-            const uint32_t row2 = has2 ? key_row(keys[i2]) : row;
-            double acc = 0.0, acc2 = 0.0;
-            for (int j = lane; j < p.d / 4; j += 32) {
-                const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j, p.sh);
-                const float4 a2 = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j, p.sh);
-                const double2 b01 = q2[2 * j], b23 = q2[2 * j + 1];
-                acc = fma(static_cast<double>(a.x), b01.x, acc);
-                acc = fma(static_cast<double>(a.y), b01.y, acc);
-                acc = fma(static_cast<double>(a.z), b23.x, acc);
-                acc = fma(static_cast<double>(a.w), b23.y, acc);
-                acc2 = fma(static_cast<double>(a2.x), b01.x, acc2);
-                acc2 = fma(static_cast<double>(a2.y), b01.y, acc2);
-                acc2 = fma(static_cast<double>(a2.z), b23.x, acc2);
-                acc2 = fma(static_cast<double>(a2.w), b23.y, acc2);
+        // keys[lo..hi) <- exact (score,row) keys.  Two candidates per warp iteration: both rows'
+        // loads are in flight before either reduction starts (the gather is latency-bound: 3 KB
+        // from a random HBM page per row).  track_min: s_min <- smallest exact score (ordered).
+        auto rescore_range = [&](int lo, int hi, bool track_min) {
+            for (int i = lo + warp; i < hi; i += 2 * nw) {
+                const int i2 = i + nw;
+                const bool has2 = i2 < hi;
+                const uint32_t row = key_row(keys[i]);
+                const uint32_t row2 = has2 ? key_row(keys[i2]) : row;
+                double acc = 0.0, acc2 = 0.0;
+                for (int j = lane; j < p.d / 4; j += 32) {
+                    const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j, p.sh);
+                    const float4 a2 = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j, p.sh);
+                    const double2 b01 = q2[2 * j], b23 = q2[2 * j + 1];
+                    acc = fma(static_cast<double>(a.x), b01.x, acc);
+                    acc = fma(static_cast<double>(a.y), b01.y, acc);
+                    acc = fma(static_cast<double>(a.z), b23.x, acc);
+                    acc = fma(static_cast<double>(a.w), b23.y, acc);
+                    acc2 = fma(static_cast<double>(a2.x), b01.x, acc2);
+                    acc2 = fma(static_cast<double>(a2.y), b01.y, acc2);
+                    acc2 = fma(static_cast<double>(a2.z), b23.x, acc2);
+                    acc2 = fma(static_cast<double>(a2.w), b23.y, acc2);
+                }
+                acc = warp_sum(acc);
+                acc2 = warp_sum(acc2);
+                if (lane == 0) {
+                    const float s1 = static_cast<float>(acc), s2 = static_cast<float>(acc2);
+                    keys[i] = make_key(s1, row);   // NaN -> high word 0
+                    if (has2) keys[i2] = make_key(s2, row2);
+                    if (track_min) {
+                        atomicMin(&s_min, order_f32(s1));                 // order(NaN) = 0: no pruning
+                        if (has2) atomicMin(&s_min, order_f32(s2));
+                    }
+                }
             }
-            acc = warp_sum(acc);
-            acc2 = warp_sum(acc2);
-            if (lane == 0) {
-                keys[i] = make_key(static_cast<float>(acc), row);   // NaN -> high word 0
-                if (has2) keys[i2] = make_key(static_cast<float>(acc2), row2);
-            }
+        };
+        int n_resc = n;
+        if (p.eps2 && n - p.k >= 64 && n <= SORT_CAP) {   // (not worth a select for a handful of rows)
+            // Two-stage rescore.  T = the rows holding the k best COARSE scores (ties included):
+            // after their exact rescore, k rows are known with exact score >= s' = min over T, so
+            // the final k-th exact score is >= s' and a member y of the final top-k has
+            // coarse(y) >= exact(y) - eps >= s' - eps: only those of the remaining rows are
+            // rescored (the list itself was cut at c_k - 2 eps; this halves the window).
+            for (int i = threadIdx.x; i < n; i += blockDim.x) sbuf[i] = keys[i];
+            if (threadIdx.x == 0) s_min = 0xFFFFFFFFu;
+            __syncthreads();
+            const unsigned long long pk = block_radix_select(sbuf, n, p.k, 4, hist, &s_prefix, &s_krem);
+            const int m1 = block_compact_disjoint(sbuf, n, true, 0u, pk, keys, s_warp);            // T
+            const int rest = block_compact_disjoint(sbuf, n, true, 0u, pk, keys + m1, s_warp, true);
+            __syncthreads();
+            rescore_range(0, m1, true);
+            __syncthreads();
+            const uint32_t omin = s_min;
+            float t2 = omin == 0u ? -INFINITY : __fsub_rd(unorder_f32(omin), 0.5f * p.eps2[slot]);
+            if (!(t2 == t2)) t2 = -INFINITY;                 // inf - inf: no usable threshold
+            t2 = nextafterf(t2, -INFINITY);                  // kept: coarse > t2
+            const int m2 = block_compact_disjoint(keys + m1, rest, false, order_f32(t2), 0ull, sbuf, s_warp);
+            for (int i = threadIdx.x; i < m2; i += blockDim.x) keys[m1 + i] = sbuf[i];
+            __syncthreads();
+            rescore_range(m1, m1 + m2, false);
+            n_resc = m1 + m2;
+        } else {
+            rescore_range(0, n, false);
         }
         if (threadIdx.x == 0 && p.gstats)
             atomicAdd(reinterpret_cast<unsigned long long*>(p.gstats + GS_RESCORED),
-                      static_cast<unsigned long long>(n));
+                      static_cast<unsigned long long>(n_resc));
         __syncthreads();
+        n = n_resc;
     }
 
     int m;   // entries to sort
