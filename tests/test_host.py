@@ -416,3 +416,37 @@ def test_indexer_host_logic_with_a_stand_in_engine(tmp_path, built, monkeypatch)
     assert small.search_knn(np.zeros((0, d), np.float32), 5) == []
     with pytest.raises(NotImplementedError):
         bi.Indexer(d, 8, 8)
+
+
+def test_iter_batches_properties(built):
+    """Property test of the streaming ingest's batcher over random shard sizes: the batches
+    concatenate back to the shards in order, every batch but the last has exactly `batch` rows,
+    ids stay aligned with rows, and batches inside one shard are zero-copy views."""
+    from hypothesis import given, settings, strategies as st
+    from b2ip.ingest import iter_batches
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(min_value=0, max_value=40), min_size=0, max_size=8),
+           st.integers(min_value=1, max_value=25))
+    def check(sizes, batch):
+        shards, start = [], 0
+        for n in sizes:
+            emb = np.arange(start, start + n, dtype=np.float32)[:, None] * np.ones((1, 3), np.float32)
+            shards.append(([f"id{start + j}" for j in range(n)], emb))
+            start += n
+        out = list(iter_batches(iter(shards), batch))
+        total = sum(sizes)
+        assert sum(len(ids) for ids, _ in out) == total
+        if total:
+            assert all(len(ids) == batch for ids, _ in out[:-1]) and 1 <= len(out[-1][0]) <= batch
+            assert [i for ids, _ in out for i in ids] == [f"id{j}" for j in range(total)]
+            rows = np.concatenate([e for _, e in out])
+            assert np.array_equal(rows[:, 0], np.arange(total, dtype=np.float32))
+            for ids, e in out:
+                assert len(ids) == e.shape[0]
+        else:
+            assert out == []
+    check()
+    big = (list(range(10)), np.zeros((10, 4), np.float32))
+    (_, first), (_, second) = list(iter_batches([big], 5))
+    assert first.base is big[1] and second.base is big[1]        # views, not copies
