@@ -450,3 +450,17 @@ def test_iter_batches_properties(built):
     big = (list(range(10)), np.zeros((10, 4), np.float32))
     (_, first), (_, second) = list(iter_batches([big], 5))
     assert first.base is big[1] and second.base is big[1]        # views, not copies
+
+
+def test_header_is_plain_c_and_declares_what_the_binding_lists(built):
+    """include/b2ip.h is the drop-in boundary: it must compile as C99 (no C++ in the ABI) and
+    declare exactly the functions the ctypes binding lists (b2ip.SYMBOLS)."""
+    import re
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "b2ip.h")
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c", hdr],
+                         capture_output=True, text=True)
+    assert out.returncode == 0 and not out.stderr.strip(), out.stderr
+    text = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+    declared = set(re.findall(r"\b(b2ip_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(built.SYMBOLS), declared ^ set(built.SYMBOLS)
