@@ -541,6 +541,9 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         }
         while (done < n) {
             int64_t s = std::min<int64_t>(slab, n - done);
+            // the kernels index tiles with 32-bit integers: keep q_tiles * x_tiles below 2^30
+            // (only reachable with hundreds of millions of short rows per shard)
+            s = std::min<int64_t>(s, std::max<int64_t>(1, (1ll << 30) / std::max(1, cp.q_tiles)) * STREAM_TILE_X);
             if (done + s < n) s = std::max<int64_t>(TILE_X, s / TILE_X * TILE_X);
             s = std::min<int64_t>(s, n - done);
             cp.x_row0 = done;
