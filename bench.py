@@ -5,18 +5,29 @@
 
 One "step" = one pass of the hot path over one batch of synthetic queries: all `n_queries`
 queries against the whole row-sharded corpus (local tcgen05 scoring + fused filter + fp32
-rescore per GPU, then the NCCL all-gather + merge when N > 1).  Default workload = BASELINE
+rescore per GPU, then the peer-direct exchange + merge when N > 1).  Default workload = BASELINE
 config 3: 21M x 768 fp32 L2-normalised synthetic corpus, 100k queries, k = 100 (fits one B200:
 64.5 GB fp32 master + 32.3 GB bf16 shadow).  The corpus is fixed as N grows -> "strong".
-`--workload c2|c4|c5` selects the other BASELINE configs for profiles/ (c4: bf16-stored
-corpus, k = 1000; c5: batches of `--n-queries` (default 64) queries, k = 10, HBM roofline);
-the driver's bench line is always the default.
 
-Prints ONE JSON line on rank 0.  `value` = queries/s with queries resident in HBM;
-`e2e` = the same through the reference-facing call with HOST buffers (H2D of the queries and
-D2H of scores+ids inside the timed region); `roofline` = the tcgen05 scoring kernel
-against the measured bf16 peak; `cpu_baseline` = the faiss-equivalent CPU oracle on the box's
-host cores on a bounded sample.  `--impl reference` times that CPU implementation alone.
+Prints ONE JSON line on rank 0:
+  value            queries/s with the queries resident in HBM (K timed steps, CUDA events, max over ranks)
+  e2e              the same through the reference-facing C-ABI call with PAGEABLE host buffers
+                   (numpy in / numpy out, H2D and D2H inside the timed region); at N > 1 through
+                   `ShardedIndex.search_host` (each rank uploads the queries and downloads its
+                   slice of the result into one host array shared by the ranks)
+  e2e_search_knn   wall time of the drop-in `Indexer.search_knn` (reference src/index.py:34-46,
+                   the region passage_retrieval.py:188-190 times): pageable float16 queries ->
+                   list of (list[str], float32 row); at N > 1 from ONE process driving all N GPUs
+                   (`Indexer(device="all")`, what an unmodified reference driver uses)
+  roofline         the tcgen05 scoring kernel against the measured bf16 peak
+  cpu_baseline     the faiss-equivalent CPU oracle on the box's host cores: a query subset
+                   against the FULL corpus, N = 1 only
+  parity_probe     fp64 brute force over every rank's shard for 32 of the timed queries,
+                   compared tie-aware with the timed result (pass / fail)
+  secondary        BASELINE configs C5 (batch 64, k = 10: HBM roofline), C2 and C4, each with
+                   its own roofline -- so the driver's records hold them at every N
+`--impl reference` times the CPU implementation alone (rank 0 only under torchrun).
+`--workload c2|c4|c5` makes another BASELINE config the primary line (for profiles/).
 """
 import argparse
 import json
@@ -35,9 +46,9 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-METRIC = "queries/sec top-100 exact IP search, 21M x 768"   # BASELINE.json metric (default workload)
 UNIT = "queries/s"
 CHUNK = 1 << 18          # rows per generated corpus chunk (seeded by global chunk index)
+PROBE_QUERIES = 32       # parity_probe: queries checked against an fp64 brute force per run
 
 # BASELINE.json configs.  bound = the roofline that applies to the scoring kernel.
 WORKLOADS = {
@@ -48,7 +59,7 @@ WORKLOADS = {
 }
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -63,17 +74,35 @@ def parse():
     ap.add_argument("--shadow", default=None, choices=["bf16", "f16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-rows", type=int, default=1 << 18)
-    ap.add_argument("--cpu-sample-queries", type=int, default=4096)
-    args = ap.parse_args()
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-search-knn", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of each e2e variant (<= --steps)")
+    ap.add_argument("--secondary-steps", type=int, default=3)
+    # CPU legs (reference arm and the cpu_baseline of the main arm)
+    ap.add_argument("--ref-queries", type=int, default=0,
+                    help="queries per CPU step (0: sized so that all warm-up + timed steps fit --ref-budget-s)")
+    ap.add_argument("--ref-budget-s", type=float, default=180.0)
+    ap.add_argument("--ref-rows", type=int, default=0,
+                    help="CPU legs on the first ROWS rows only (0 = the full corpus; >0 is reported as a scaled estimate)")
+    ap.add_argument("--corpus-file", default=None, help="raw float32 [n_corpus, d] file to map instead of generating")
+    ap.add_argument("--extra-cpu-legs", default="", help="e.g. 'c5:1,c5:64': extra CPU timings over the same corpus")
+    ap.add_argument("--cpu-baseline-queries", type=int, default=512)
+    args = ap.parse_args(argv)
     w = WORKLOADS[args.workload]
     for key in ("n_corpus", "n_queries", "k", "store"):
         if getattr(args, key) is None:
             setattr(args, key, w[key])
     args.bound = w["bound"]
-    if args.workload == "c5" and args.steps == 3 and "--steps" not in sys.argv:
+    if args.workload == "c5" and "--steps" not in (argv if argv is not None else sys.argv):
         args.steps = 200      # latency per batch over >= 200 batches after warm-up
     return args
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def load_peaks():
@@ -84,6 +113,19 @@ def load_peaks():
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, \
             "fallback (B200_PROFILING.md)"
+
+
+def profile_traffic(name):
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture:
+    a constant read from profiles/, NOT measured by this run (ncu cannot run inside a bench)."""
+    for cand in (name.replace("r1", "r2", 1), name):
+        try:
+            with open(os.path.join(ROOT, "profiles", cand)) as f:
+                prof = json.load(f)
+            return prof, cand
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -152,71 +194,365 @@ def gen_rows(torch, lo, hi, d, seed_base, device):
         yield max(lo, c0), x[a:b]
 
 
-def cpu_reference_qps(args, sample_rows_host, sample_q_host, steps, warmup):
-    """faiss-IndexFlatIP-equivalent CPU search (oracle/flatip_oracle.c, OpenBLAS sgemm blocks +
-    reservoir handler) with all host threads, on the bounded sample; QPS is scaled to the full
-    corpus size (cost is linear in rows at fixed nq)."""
-    from oracle import flatip_oracle as fo
-    ts = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        fo.search(sample_q_host, sample_rows_host, args.k)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            ts.append(dt)
-    t = sum(ts) / len(ts)
-    scale = args.n_corpus / sample_rows_host.shape[0]
-    qps = sample_q_host.shape[0] / (t * scale)
-    info = {
-        "value": qps, "unit": UNIT, "cores": fo.num_threads(), "kind": "port",
-        "sample": (f"{sample_q_host.shape[0]} queries x {sample_rows_host.shape[0]} rows of the same "
-                   f"synthetic corpus, {t:.2f} s per pass, scaled x{scale:.1f} to {args.n_corpus} rows; "
-                   f"faiss-cpu 1.8.0 not installable offline -> CPU restatement, BLAS: {fo.blas_description()}"),
+def gen_queries(torch, nq, d, device):
+    gen = torch.Generator(device=device).manual_seed(4321)
+    q = torch.randn((nq, d), generator=gen, device=device, dtype=torch.float32)
+    q /= q.norm(dim=1, keepdim=True)
+    return q
+
+
+def metric_name(n_corpus, k, d):
+    return f"queries/sec top-{k} exact IP search, {n_corpus / 1e6:g}M x {d}"
+
+
+def workload_config(args, world, name=None, n_corpus=None, n_queries=None, k=None, store=None):
+    name = name or args.workload
+    n_corpus = n_corpus or args.n_corpus
+    n_queries = n_queries or args.n_queries
+    k = k or args.k
+    store = store or args.store
+    op = store if store != "f32" else (args.shadow or "bf16")
+    stored = {"f32": "fp32", "bf16": "bf16-stored", "f16": "fp16-stored"}[store]
+    return {
+        "workload": (f"{name.upper()}: {n_corpus} x {args.d} {stored} synthetic L2-normalised corpus, "
+                     f"{n_queries} queries, k={k}"),
+        "n_corpus": n_corpus, "n_queries": n_queries, "k": k, "d": args.d,
+        "parallelism": f"row-shard x{world} (one process per GPU; peer-direct exchange over NVLink + merge, "
+                       "NCCL all-gather as fallback)",
+        "l2": f"inputs exceed L2: every step streams the whole {op} operand copy of the corpus (2*d bytes/row)",
+        "coarse": f"tcgen05 kind::f16 {op} operands, fp32 accumulate; fp32 rescore (fp64 accumulate)",
     }
-    return info, t
+
+
+# =============================================================================== CPU legs
+def _host_corpus(args, np):
+    """The synthetic corpus in host memory as float32 [rows, d] + a note saying where it came from."""
+    n, d = args.n_corpus, args.d
+    rows = args.ref_rows if 0 < args.ref_rows < n else n
+    if args.corpus_file:
+        x = np.memmap(args.corpus_file, dtype=np.float32, mode="r", shape=(n, d))
+        return x[:rows], "the rows the GPU index holds (exported to host memory by the main arm)"
+    try:
+        import torch
+        cuda = torch.cuda.is_available()
+    except Exception:
+        cuda = False
+    x = np.empty((rows, d), dtype=np.float32)
+    if cuda:
+        # the generator bench.py's GPU arm uses (same seeds -> the same corpus), copied to the host
+        dev = torch.device("cuda", 0)
+        pin = torch.empty((CHUNK, d), dtype=torch.float32, pin_memory=True)
+        for g0, r in gen_rows(torch, 0, rows, d, 1234, dev):
+            m = r.shape[0]
+            pin[:m].copy_(r)
+            torch.cuda.synchronize()
+            x[g0:g0 + m] = pin[:m].numpy()
+        del pin
+        torch.cuda.empty_cache()
+        return x, "the same synthetic corpus as the GPU arm (torch CUDA generator, seed 1234, copied to host)"
+    from concurrent.futures import ThreadPoolExecutor
+
+    def fill(c):
+        lo, hi = c * CHUNK, min(rows, (c + 1) * CHUNK)
+        r = np.random.Generator(np.random.Philox(key=1234 * 1000003 + c)).standard_normal((hi - lo, d), dtype=np.float32)
+        r /= np.linalg.norm(r, axis=1, keepdims=True)
+        x[lo:hi] = r
+    with ThreadPoolExecutor(max_workers=host_cores()) as ex:
+        list(ex.map(fill, range((rows + CHUNK - 1) // CHUNK)))
+    return x, "a synthetic L2-normalised Gaussian corpus of the same shape (numpy Philox; no CUDA device for the GPU arm's generator)"
+
+
+def _host_queries(args, np, nq):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return gen_queries(torch, max(nq, 64), args.d, torch.device("cuda", 0))[:nq].cpu().numpy()
+    except Exception:
+        pass
+    q = np.random.Generator(np.random.Philox(key=4321)).standard_normal((nq, args.d), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return q
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (restated, see
-    oracle/), rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path -- `Indexer.search_knn`
+    over `faiss.IndexFlatIP.search` (src/index.py:34-46) -- as restated in oracle/ (faiss-cpu 1.8.0
+    is not installable offline; real faiss is used when importable).  Rank 0 only.  Every step
+    searches `ref_queries` queries against the FULL corpus held in host memory (BASELINE.md 3);
+    `value` is the measured queries/s of those steps, `ms_per_step` their measured duration."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    cores = host_cores()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm gets every host core, set BEFORE numpy /
+    # OpenBLAS / libgomp are loaded
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cores)
     import numpy as np
-    rng = np.random.default_rng(1234)
-    rows = rng.standard_normal((args.cpu_sample_rows, args.d), dtype=np.float32)
-    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
-    q = rng.standard_normal((args.cpu_sample_queries, args.d), dtype=np.float32)
-    q /= np.linalg.norm(q, axis=1, keepdims=True)
-    info, t = cpu_reference_qps(args, rows, q, args.steps, args.warmup)
+    from oracle import flatip_oracle as fo
+    t_gen = time.perf_counter()
+    x, corpus_note = _host_corpus(args, np)
+    t_gen = time.perf_counter() - t_gen
+    rows = x.shape[0]
+    scale = args.n_corpus / rows
+    n_pass = args.steps + args.warmup
+    # calibration: a short search tells how many queries fit the time budget
+    qcal = _host_queries(args, np, 256)
+    cal_rows = min(rows, 1 << 17)
+    fo.restatement_search(qcal[:64], x[:cal_rows], args.k)
+    t0 = time.perf_counter()
+    fo.restatement_search(qcal, x[:cal_rows], args.k)
+    rate = 2.0 * 256 * cal_rows * args.d / (time.perf_counter() - t0)
+    nq_s = args.ref_queries
+    if nq_s <= 0:
+        per_pass = args.ref_budget_s / max(1, n_pass)
+        nq_s = int(per_pass * rate / (2.0 * rows * args.d)) // 32 * 32
+        nq_s = max(32, min(2048, nq_s))
+    nq_s = min(nq_s, args.n_queries)
+    q = _host_queries(args, np, nq_s)
+    ix = fo.make_index(x)            # faiss.IndexFlatIP(d) + add (real faiss when importable)
+    ts = []
+    for i in range(n_pass):
+        t0 = time.perf_counter()
+        ix.search(q, args.k)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            ts.append(dt)
+    t = sum(ts) / len(ts)
+    qps = nq_s / t / scale
+    extra = []
+    for leg in [s for s in args.extra_cpu_legs.split(",") if s]:
+        name, b = leg.split(":")
+        w, b = WORKLOADS[name], int(b)
+        qb = _host_queries(args, np, b)
+        t0 = time.perf_counter()
+        ix.search(qb, w["k"])
+        tb = time.perf_counter() - t0
+        extra.append({"workload": name, "batch": b, "k": w["k"], "ms_per_batch": tb * 1e3 * scale,
+                      "value": b / tb / scale, "unit": UNIT,
+                      "threads_used": min(b, cores) if b < 20 else cores,
+                      "note": ("faiss's sequential path (nq < 20): one thread per query" if b < 20
+                               else "sgemm block path")})
+    info = {
+        "value": qps, "unit": UNIT, "cores": fo.num_threads(), "kind": fo.backend_kind(),
+        "sample": (f"{nq_s} queries x {rows} rows ({'the FULL corpus' if rows == args.n_corpus else 'a row subset'}) "
+                   f"per step, {t:.2f} s per step, k={args.k}; {corpus_note}; {fo.backend_description()}; "
+                   f"host threads {cores} (OMP_NUM_THREADS/OPENBLAS_NUM_THREADS forced before load); the "
+                   "restatement's sgemm+handler throughput stops scaling at ~16 threads"),
+        "queries_per_step": nq_s, "rows": rows, "seconds_per_step": t,
+        "gflops": 2.0 * nq_s * rows * args.d / t / 1e9, "corpus_to_host_s": t_gen,
+        "scaled_to": None if rows == args.n_corpus else {
+            "n_corpus": args.n_corpus, "factor": scale,
+            "note": "value = measured queries/s on the row subset / factor (cost is linear in rows)"},
+        "extra_legs": extra,
+    }
     line = {
-        "impl": "reference", "metric": metric_name(args), "value": info["value"], "unit": UNIT,
+        "impl": "reference", "metric": metric_name(args.n_corpus, args.k, args.d), "value": qps, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * args.n_queries / info["value"], "higher_is_better": True,
+        "ms_per_step": 1e3 * t, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": info,
-        "e2e": {"value": info["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def metric_name(args):
-    m = args.n_corpus / 1e6
-    return f"queries/sec top-{args.k} exact IP search, {m:g}M x {args.d}"
+def cpu_baseline_subprocess(args, corpus_file, extra_legs):
+    """The CPU legs of the main arm run in a fresh interpreter (`--impl reference`): thread
+    counts of OpenBLAS / libgomp are fixed when those libraries load, and this process has
+    already loaded torch."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--workload", args.workload, "--n-corpus", str(args.n_corpus), "--k", str(args.k), "--d", str(args.d),
+           "--ref-queries", str(min(args.cpu_baseline_queries, args.n_queries)),
+           "--corpus-file", corpus_file, "--extra-cpu-legs", extra_legs]
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    env["CUDA_VISIBLE_DEVICES"] = ""          # the CPU legs must not touch the GPU being measured
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
+    if out.returncode != 0:
+        return {"error": (out.stderr or out.stdout)[-400:]}
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    return line["cpu_baseline"]
 
 
-def workload_config(args, world):
-    op = args.store if args.store != "f32" else (args.shadow or "bf16")
-    stored = {"f32": "fp32", "bf16": "bf16-stored", "f16": "fp16-stored"}[args.store]
+# =============================================================================== GPU arm
+class Dist:
+    """barrier / reductions over the ranks (identity at world 1)."""
+
+    def __init__(self, torch, dist, world, dev):
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _red(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX) if self.world > 1 else x
+
+    def sum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM) if self.world > 1 else x
+
+
+STAT_KEYS = ("coarse_ms", "coarse_flops", "coarse_launches", "launches", "candidates", "rescored", "fallback",
+             "slabs", "refresh_ms", "finalize_ms", "device_ms", "max_err_over_eps", "bound_violations")
+
+
+def timed_device_steps(torch, D, index, q_dev, k, steps, warmup, world, sample_clocks_on=None):
+    """W untimed + K timed searches with device-resident queries.  Returns per-step ms (max over
+    ranks), the summed engine stats of the timed steps, the last result (scores, rows, (q_lo, q_hi))
+    of the queries this rank owns, and the clock samples."""
+    agg = {key: 0.0 for key in STAT_KEYS}
+
+    def step():
+        # world > 1: the result stays partitioned over the ranks by query (rank r holds the global
+        # top-k of the queries it owns) -- every query is merged once, nothing is replicated
+        res = index.search_owned(q_dev, k)
+        st = index.engine.stats()
+        agg["coarse_ms"] += st["coarse_ms"]; agg["coarse_flops"] += st["coarse_flops"]
+        agg["coarse_launches"] += st["coarse_launches"]
+        # all-gather path: + the NCCL kernel and the merge kernel; the peer-direct exchange's
+        # launches are already in the library's count
+        agg["launches"] += st["total_launches"] + (2 if world > 1 and getattr(index, "exchange_searches", 0) == 0 else 0)
+        agg["candidates"] += st["candidates"]; agg["rescored"] += st["rescored"]
+        agg["fallback"] += st["fallback_queries"]; agg["slabs"] += st["slabs"]
+        agg["refresh_ms"] += st["refresh_ms"]; agg["finalize_ms"] += st["finalize_ms"]
+        agg["device_ms"] += st["total_ms"]
+        agg["max_err_over_eps"] = max(agg["max_err_over_eps"], st.get("max_err_over_eps", 0.0))
+        agg["bound_violations"] += st.get("bound_violations", 0)
+        return res
+
+    for _ in range(warmup):
+        step()
+    for key in agg:
+        agg[key] = 0.0
+    sampler = ClockSampler(sample_clocks_on) if sample_clocks_on is not None else None
+    D.barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        last = step()
+    e1.record()
+    D.barrier()
+    clocks = sampler.finish() if sampler else None
+    ms = D.max(e0.elapsed_time(e1))
+    return ms / steps, agg, last, clocks
+
+
+def roofline_of(args, D, agg, steps, ms_per_step, rows_local, nq, bound, d):
+    peaks, peak_src = load_peaks()
+    coarse_ms = D.max(agg["coarse_ms"])
+    launches = max(1, int(agg["coarse_launches"]))
+    if bound == "tensor":
+        achieved = agg["coarse_flops"] / (agg["coarse_ms"] / 1e3) / 1e12 if agg["coarse_ms"] > 0 else 0.0
+        achieved = -D.max(-achieved)     # slowest rank
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        prof, src = profile_traffic("r1_coarse_ncu.json")
+        return {
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": (prof["dram_bytes_read"] + prof["dram_bytes_write"]) if prof else None,
+            "traffic_note": (f"CONSTANT from profiles/{src} (one `ncu --set full` capture of {prof['launch']}: "
+                             f"{prof['flops']:.3e} FLOP in {prof['duration_ms']:.1f} ms), not measured by this run")
+            if prof else None,
+            "kernel": "coarse_filter_pair_kernel (tcgen05.mma.cta_group::2 kind::f16, fused threshold filter)",
+            "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a multi-second step)",
+            "burst_peak": peaks.get("bf16_tflops"),
+            "flops_per_launch_avg": agg["coarse_flops"] / launches,
+            "launches": int(agg["coarse_launches"]), "kernel_ms_per_step": coarse_ms / steps,
+            "kernel_share_of_step": coarse_ms / steps / ms_per_step if ms_per_step > 0 else None,
+        }
+    # small batches: the streaming kernel reads the 16-bit operand copy of the shard once per batch
+    # -> HBM-bound.  Algorithmic bytes = rows * d * 2 (what MUST be read); SURVEY 8d's figure for an
+    # fp32-stored corpus (rows * d * 4) is reported next to it.
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_rank = rows_local * d * 2.0 * steps
+    gbs = bytes_rank / (agg["coarse_ms"] / 1e3) / 1e9 if agg["coarse_ms"] > 0 else 0.0
+    gbs = -D.max(-gbs)
+    prof, src = profile_traffic("r1c_stream_ncu.json")
+    whole = rows_local * d * 2.0 / (ms_per_step / 1e3) / 1e9
     return {
-        "workload": (f"{args.workload.upper()}: {args.n_corpus} x {args.d} {stored} synthetic L2-normalised corpus, "
-                     f"{args.n_queries} queries, k={args.k}"),
-        "n_corpus": args.n_corpus, "n_queries": args.n_queries, "k": args.k, "d": args.d,
-        "parallelism": f"row-shard x{world} (one process per GPU, NCCL all-gather + merge)",
-        "l2": f"inputs exceed L2: every step streams the whole {op} operand copy of the corpus (2*d bytes/row)",
-        "coarse": f"tcgen05 kind::f16 {op} operands, fp32 accumulate; fp32 rescore (fp64 accumulate)",
+        "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+        "traffic": (prof["dram_bytes_read"] + prof["dram_bytes_write"]) if prof else None,
+        "traffic_note": (f"CONSTANT from profiles/{src} (one `ncu --set full` capture of {prof['launch']}: "
+                         f"{prof['algorithmic_bytes']:.4e} algorithmic bytes in {prof['duration_ms']:.3f} ms), "
+                         "not measured by this run") if prof else None,
+        "kernel": ("coarse_stream_kernel (corpus tile on the MMA's M side, resident queries, TMA-streamed 16-bit rows)"
+                   if nq <= 64 else "coarse_filter_kernel<false> (TMA-streamed 16-bit corpus tiles, fused filter)"),
+        "peak_source": peak_src + " hbm_gbs (copy bandwidth)",
+        "bytes_per_launch_avg": bytes_rank / launches,
+        "launches": int(agg["coarse_launches"]), "kernel_ms_per_step": coarse_ms / steps,
+        "kernel_share_of_step": coarse_ms / steps / ms_per_step if ms_per_step > 0 else None,
+        "whole_batch_gbs_16bit": whole, "whole_batch_frac_16bit": whole / peak,
+        "whole_batch_gbs_fp32_bytes_survey8d": 2.0 * whole,
+        "ms_per_batch": ms_per_step,
     }
+
+
+def parity_probe(torch, dist, D, res, q_dev, k, d, lo, hi, world, rank, dev, rows_fn, rtol=1e-5):
+    """fp64 brute force over this rank's shard for the first PROBE_QUERIES queries, all-gathered
+    and merged, against the timed result: identical id sets except for ties within `rtol`
+    relative of the k-th score, scores within `rtol` relative (the north_star tolerance)."""
+    nqp = min(PROBE_QUERIES, q_dev.shape[0])
+    qs = q_dev[:nqp].double()
+    best_s = torch.full((nqp, 0), 0.0, dtype=torch.float64, device=dev)
+    best_i = torch.zeros((nqp, 0), dtype=torch.int64, device=dev)
+    for g0, rows in rows_fn(lo, hi):
+        s = qs @ rows.double().T
+        ids = torch.arange(g0, g0 + rows.shape[0], device=dev).expand(nqp, -1)
+        cs, ci = torch.cat([best_s, s], dim=1), torch.cat([best_i, ids], dim=1)
+        top = torch.topk(cs, min(k, cs.shape[1]), dim=1)
+        best_s, best_i = top.values, torch.gather(ci, 1, top.indices)
+    if best_s.shape[1] < k:       # a shard with fewer than k rows
+        pad = k - best_s.shape[1]
+        best_s = torch.cat([best_s, torch.full((nqp, pad), -float("inf"), dtype=torch.float64, device=dev)], 1)
+        best_i = torch.cat([best_i, torch.full((nqp, pad), -1, dtype=torch.int64, device=dev)], 1)
+    if world > 1:
+        gs = [torch.empty_like(best_s) for _ in range(world)]
+        gi = [torch.empty_like(best_i) for _ in range(world)]
+        dist.all_gather(gs, best_s.contiguous())
+        dist.all_gather(gi, best_i.contiguous())
+        cs, ci = torch.cat(gs, 1), torch.cat(gi, 1)
+        top = torch.topk(cs, k, dim=1)
+        best_s, best_i = top.values, torch.gather(ci, 1, top.indices)
+    Dg, Ig, (q_lo, q_hi) = res                   # this rank's queries [q_lo, q_hi) of the search
+    a0, a1 = min(q_lo, nqp), min(q_hi, nqp)        # probe queries this rank holds the answer of
+    ours_s, ours_i = Dg[a0 - q_lo:a1 - q_lo].double(), Ig[a0 - q_lo:a1 - q_lo]
+    best_s, best_i = best_s[a0:a1], best_i[a0:a1]
+    rel = ((ours_s - best_s).abs() / best_s.abs().clamp_min(1e-30)).max().item() if a1 > a0 else 0.0
+    ok = rel <= rtol
+    tie_swaps = 0
+    bs, bi, oi = best_s.cpu(), best_i.cpu(), ours_i.cpu()
+    os_ = ours_s.cpu()
+    for j in range(a1 - a0):
+        a, b = set(oi[j].tolist()), set(bi[j].tolist())
+        if a == b:
+            continue
+        tie_swaps += 1
+        kth = float(bs[j, -1])
+        # an id on one side only must tie with the k-th score: its own score is on its side's list
+        for r in a - b:
+            sc = float(os_[j][oi[j] == r][0])
+            ok = ok and abs(sc - kth) <= rtol * abs(kth)
+        for r in b - a:
+            sc = float(bs[j][bi[j] == r][0])
+            ok = ok and abs(sc - kth) <= rtol * abs(kth)
+    rel = D.max(rel)
+    tie_swaps = int(D.sum(tie_swaps))
+    ok = D.sum(0.0 if ok else 1.0) == 0.0
+    return {"queries": nqp, "max_rel_score_err": rel, "queries_with_tie_swaps": tie_swaps, "rtol": rtol,
+            "checked_against": "fp64 torch brute force over the full corpus (every rank's shard, all-gathered); "
+                               "each rank checks the probe queries whose result it owns",
+            "pass": bool(ok)}
 
 
 def main():
@@ -234,7 +570,8 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from b2ip import ShardedIndex, shard_bounds
+    from b2ip import Engine, ShardedIndex, shard_bounds
+    from b2ip.indexer import Indexer
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -245,211 +582,250 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    D = Dist(torch, dist, world, dev)
 
     N, nq, k, d = args.n_corpus, args.n_queries, args.k, args.d
     lo, hi = shard_bounds(N, world, rank)
-    index = ShardedIndex(d, device=local_rank, store=args.store)
-    if args.shadow is not None:
-        index.engine.set_option("shadow_f16", int(args.shadow == "f16"))
-    index.engine.reserve(hi - lo)
+
+    def build_index(store, n_rows, shadow=None):
+        """Row shard [lo,hi) of the first n_rows rows of the synthetic corpus on this rank's GPU."""
+        a, b = shard_bounds(n_rows, world, rank)
+        ix = ShardedIndex(d, device=local_rank, store=store)
+        if shadow is not None:
+            ix.engine.set_option("shadow_f16", int(shadow == "f16"))
+        ix.engine.reserve(b - a)
+        for g0, rows in gen_rows(torch, a, b, d, 1234, dev):
+            ix.add_local(rows, g0)
+        ix.engine.use_torch_stream()
+        return ix, a, b
+
     t_ing = time.perf_counter()
-    sample_host = None
-    for g0, rows in gen_rows(torch, lo, hi, d, 1234, dev):
-        index.add_local(rows, g0)
-        if rank == 0 and sample_host is None and not args.no_cpu_baseline and world == 1:
-            sample_host = rows[:min(args.cpu_sample_rows, rows.shape[0])].cpu().numpy()
-    if rank == 0 and sample_host is not None and sample_host.shape[0] < args.cpu_sample_rows:
-        extra = [sample_host]
-        need = args.cpu_sample_rows - sample_host.shape[0]
-        for g0, rows in gen_rows(torch, CHUNK, min(N, CHUNK + need), d, 1234, dev):
-            extra.append(rows.cpu().numpy())
-        sample_host = np.concatenate(extra)[:args.cpu_sample_rows]
+    index, lo, hi = build_index(args.store, N, args.shadow)
     torch.cuda.synchronize()
     t_ing = time.perf_counter() - t_ing
-
-    gen = torch.Generator(device=dev).manual_seed(4321)
-    q_dev = torch.randn((nq, d), generator=gen, device=dev, dtype=torch.float32)
-    q_dev /= q_dev.norm(dim=1, keepdim=True)
-    q_pin = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
-    q_pin.copy_(q_dev)
-    D_pin = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
-    I_pin = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
-    torch.cuda.synchronize()
-    index.engine.use_torch_stream()
+    q_dev = gen_queries(torch, nq, d, dev)
 
     # ---------------------------------------------------------------- device-resident timing
-    agg = {"coarse_ms": 0.0, "coarse_flops": 0.0, "coarse_launches": 0, "launches": 0,
-           "candidates": 0, "rescored": 0, "fallback": 0, "slabs": 0, "refresh_ms": 0.0,
-           "finalize_ms": 0.0, "device_ms": 0.0}
-
-    def step_device():
-        D, I = index.search(q_dev, k)
-        st = index.engine.stats()
-        agg["coarse_ms"] += st["coarse_ms"]; agg["coarse_flops"] += st["coarse_flops"]
-        agg["coarse_launches"] += st["coarse_launches"]
-        # all-gather path: + the NCCL kernel and the merge kernel; the peer-direct exchange's two
-        # launches (signal, waiting merge) are already in the library's count
-        agg["launches"] += st["total_launches"] + (2 if world > 1 and getattr(index, "exchange_searches", 0) == 0 else 0)
-        agg["candidates"] += st["candidates"]; agg["rescored"] += st["rescored"]
-        agg["fallback"] += st["fallback_queries"]; agg["slabs"] += st["slabs"]
-        agg["refresh_ms"] += st["refresh_ms"]; agg["finalize_ms"] += st["finalize_ms"]
-        agg["device_ms"] += st["total_ms"]
-        return D, I
-
-    for _ in range(args.warmup):
-        step_device()
-    for key in agg:
-        agg[key] = 0
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        D_last, I_last = step_device()
-    e1.record()
-    barrier()
-    clocks = sampler.finish()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = ms / args.steps
+    ms_per_step, agg, last, clocks = timed_device_steps(
+        torch, D, index, q_dev, k, args.steps, args.warmup, world, sample_clocks_on=local_rank)
+    D_last, I_last, (own_lo, own_hi) = last
     value = nq / (ms_per_step / 1e3)
+    roofline = roofline_of(args, D, agg, args.steps, ms_per_step, hi - lo, nq, args.bound, d)
+    probe = parity_probe(torch, dist, D, last, q_dev, k, d, lo, hi, world, rank, dev,
+                         lambda a, b: gen_rows(torch, a, b, d, 1234, dev))
+    # order-independent digest of the last step's results, summed over the ranks' query slices:
+    # the id sums are identical at every N (the sharded search returns the single-GPU answer),
+    # so the scaling runs check each other
+    ck = torch.stack([I_last.sum(), (I_last * torch.arange(1, k + 1, device=dev)).sum()])
+    sc = D_last.double().sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(ck)
+        dist.all_reduce(sc)
+    checksum = {"ids_sum": int(ck[0].item()), "ids_weighted": int(ck[1].item()),
+                "scores_sum_f64": float(sc.item())}
+    launches = int(D.sum(agg["launches"]))
 
-    # ---------------------------------------------------------------- end-to-end timing
+    # ---------------------------------------------------------------- end-to-end: C ABI, pageable host buffers
     e2e = None
+    n_e2e = max(1, min(args.e2e_steps, args.steps))
+    q_host = q_dev.cpu().numpy()                      # pageable numpy: what the reference hands over
     if not args.no_e2e:
-        def step_e2e():
-            if world == 1:
-                # the reference-facing call: host buffers across the C ABI
-                index.engine.search(q_pin.numpy(), k, out=(D_pin.numpy(), I_pin.numpy()))
-            else:
-                qd = q_pin.to(dev, non_blocking=True)
-                D, I = index.search(qd, k)
-                D_pin.copy_(D, non_blocking=True)
-                I_pin.copy_(I, non_blocking=True)
-                torch.cuda.synchronize()
-        for _ in range(max(1, args.warmup - 2)):
-            step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(args.steps):
-            step_e2e()
-        e1.record()
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        ms_e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
-        e2e = {"value": nq / (ms_e / args.steps / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": world * nq * d * 4, "d2h_bytes_per_step": world * nq * k * 12,
-               "ms_per_step": ms_e / args.steps,
-               "call": "b2ip_search(mem=HOST) via ctypes" if world == 1 else "ShardedIndex.search + pinned H2D/D2H"}
+        shm = None
+        if world == 1:
+            D_host = np.empty((nq, k), dtype=np.float32)
+            I_host = np.empty((nq, k), dtype=np.int64)
 
-    # ---------------------------------------------------------------- roofline of the scoring kernel
-    peaks, peak_src = load_peaks()
-    coarse_ms = max_over_ranks(agg["coarse_ms"])
-    flops_rank = agg["coarse_flops"]
-    achieved = flops_rank / (agg["coarse_ms"] / 1e3) / 1e12 if agg["coarse_ms"] > 0 else 0.0
-    achieved = -max_over_ranks(-achieved)     # slowest rank
-    traffic, traffic_note = None, None
-    if args.bound == "tensor":
-        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-        try:   # dram bytes of the scoring kernel from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r1_coarse_ncu.json")) as f:
-                prof = json.load(f)
-            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
-            traffic_note = (f"ncu capture of one launch ({prof['launch']}, {prof['flops']:.3e} FLOP, "
-                            f"{prof['duration_ms']:.1f} ms): dram read+write bytes; {prof['source']}")
-        except Exception:
-            pass
-        roofline = {
-            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-            "kernel": "coarse_filter_pair_kernel (tcgen05.mma.cta_group::2 kind::f16, fused threshold filter)",
-            "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a multi-second step)",
-            "burst_peak": peaks.get("bf16_tflops"),
-            "flops_per_launch_avg": flops_rank / max(1, agg["coarse_launches"]),
-            "launches": agg["coarse_launches"], "kernel_ms_per_step": coarse_ms / args.steps,
-            "kernel_share_of_step": coarse_ms / ms if ms > 0 else None,
+            def step_e2e():
+                index.engine.search(q_host, k, out=(D_host, I_host))   # b2ip_search(mem=HOST) via ctypes
+        else:
+            # one host result array shared by the ranks (POSIX shared memory): rank r downloads
+            # the queries' slice it owns, rank 0 sees the whole answer
+            tag = os.environ.get("MASTER_PORT", "0")
+            shm = [f"/dev/shm/b2ip_bench_{tag}_{n}.bin" for n in ("D", "I")]
+            if rank == 0:
+                np.memmap(shm[0], dtype=np.float32, mode="w+", shape=(nq, k)).flush()
+                np.memmap(shm[1], dtype=np.int64, mode="w+", shape=(nq, k)).flush()
+            D.barrier()
+            D_host = np.memmap(shm[0], dtype=np.float32, mode="r+", shape=(nq, k))
+            I_host = np.memmap(shm[1], dtype=np.int64, mode="r+", shape=(nq, k))
+
+            def step_e2e():
+                index.search_host(q_host, k, out=(D_host, I_host))
+        step_e2e()
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            step_e2e()
+        D.barrier()
+        ms_e = D.max((time.perf_counter() - t0) * 1e3)
+        same = bool(np.array_equal(I_host[:8], I_last[:8].cpu().numpy())) if rank == 0 else None
+        e2e = {"value": nq / (ms_e / n_e2e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": nq * d * 4 * world, "d2h_bytes_per_step": nq * k * 12,
+               "ms_per_step": ms_e / n_e2e, "steps": n_e2e, "host_buffers": "pageable numpy (not page-locked)",
+               "timing": "host wall clock around the calls, max over ranks",
+               "matches_device_result": same,
+               "call": ("Engine.search(numpy) -> b2ip_search_ex(mem=HOST) via ctypes" if world == 1 else
+                        "ShardedIndex.search_host: every rank uploads the queries, searches, and downloads the "
+                        "result slice it owns into one shared host array")}
+        if shm and rank == 0:
+            del D_host, I_host
+            for f in shm:
+                try:
+                    os.unlink(f)
+                except OSError:
+                    pass
+
+    # ---------------------------------------------------------------- secondary workloads
+    secondary = {}
+
+    def run_secondary(name, ix, rows_local, nq2, k2, bound, steps2, warm2, n_rows):
+        q2 = q_dev[:nq2].contiguous()
+        ms2, agg2, res2, _ = timed_device_steps(torch, D, ix, q2, k2, steps2, warm2, world)
+        a, b = shard_bounds(n_rows, world, rank)
+        pr = parity_probe(torch, dist, D, res2, q2, k2, d, a, b, world, rank, dev,
+                          lambda x, y: _probe_rows(x, y, ix))
+        secondary[name] = {
+            "metric": metric_name(n_rows, k2, d), "value": nq2 / (ms2 / 1e3), "unit": UNIT,
+            "ms_per_step": ms2, "steps": steps2, "warmup": warm2, "n_queries": nq2, "k": k2,
+            "store": ix.engine.store, "rows_per_gpu": rows_local,
+            "roofline": roofline_of(args, D, agg2, steps2, ms2, rows_local, nq2, bound, d),
+            "parity_probe": pr,
+            "rescored_per_query": agg2["rescored"] / steps2 / nq2,
+            "fallback_queries": int(agg2["fallback"]),
+            "rank0_ms_per_step": {"coarse": agg2["coarse_ms"] / steps2, "refresh": agg2["refresh_ms"] / steps2,
+                                  "finalize": agg2["finalize_ms"] / steps2, "search_device_total": agg2["device_ms"] / steps2},
         }
-    else:
-        # small batches: the same kernel streams the 16-bit operand copy of the shard once per
-        # batch -> HBM-bound.  Algorithmic bytes = rows * d * 2 (what MUST be read); SURVEY 8d's
-        # figure for an fp32-stored corpus (rows * d * 4) is reported next to it.
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        bytes_rank = (hi - lo) * d * 2.0 * args.steps
-        gbs = bytes_rank / (agg["coarse_ms"] / 1e3) / 1e9 if agg["coarse_ms"] > 0 else 0.0
-        gbs = -max_over_ranks(-gbs)
-        try:   # dram bytes of the streaming kernel from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r1c_stream_ncu.json")) as f:
-                prof = json.load(f)
-            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
-            traffic_note = (f"ncu capture of one launch ({prof['launch']}, {prof['algorithmic_bytes']:.4e} "
-                            f"algorithmic bytes, {prof['duration_ms']:.3f} ms): dram read+write bytes; {prof['source']}")
-        except Exception:
-            pass
-        roofline = {
-            "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-            "traffic": traffic, "traffic_note": traffic_note,
-            "kernel": ("coarse_stream_kernel (corpus tile on the MMA's M side, resident queries, TMA-streamed 16-bit rows)"
-                       if nq <= 64 else "coarse_filter_kernel<false> (TMA-streamed 16-bit corpus tiles, fused filter)"),
-            "peak_source": peak_src + " hbm_gbs (copy bandwidth)",
-            "bytes_per_launch_avg": bytes_rank / max(1, agg["coarse_launches"]),
-            "launches": agg["coarse_launches"], "kernel_ms_per_step": coarse_ms / args.steps,
-            "kernel_share_of_step": coarse_ms / ms if ms > 0 else None,
-            "whole_batch_gbs_16bit": (hi - lo) * d * 2.0 / (ms_per_step / 1e3) / 1e9,
-            "whole_batch_gbs_fp32_bytes_survey8d": (hi - lo) * d * 4.0 / (ms_per_step / 1e3) / 1e9,
-            "ms_per_batch": ms_per_step,
-        }
+
+    def _probe_rows(a, b, ix):
+        # a bf16 / fp16 store is exact w.r.t. the STORED values: the probe sees those ("same inputs")
+        for g0, rows in gen_rows(torch, a, b, d, 1234, dev):
+            if ix.engine.store == "bf16":
+                rows = rows.bfloat16().float()
+            elif ix.engine.store == "f16":
+                rows = rows.half().float()
+            yield g0, rows
+
+    if not args.no_secondary and args.workload == "c3":
+        s2 = max(1, args.secondary_steps)
+        # C5: latency regime on the same index (batch 64, k = 10), >= 200 batches
+        run_secondary("c5_batch64_k10", index, hi - lo, 64, 10, "hbm", 200, 20, N)
+        run_secondary("c5_batch1_k10", index, hi - lo, 1, 10, "hbm", 200, 20, N)
+        # C2: 1M x 768, 10k queries (a single-GPU config: rank 0's GPU alone at N > 1 would idle
+        # the others, so it is sharded like the rest and stays comparable at N = 1)
+        ix2, a2, b2 = build_index("f32", WORKLOADS["c2"]["n_corpus"])
+        run_secondary("c2_1M_10k_k100", ix2, b2 - a2, 10_000, 100, "tensor", 20, 3, WORKLOADS["c2"]["n_corpus"])
+        ix2.engine.close()
+        del ix2
+        # C4: bf16-stored corpus, k = 1000
+        ix4, a4, b4 = build_index("bf16", N)
+        run_secondary("c4_bf16_store_k1000", ix4, b4 - a4, nq, 1000, "tensor", s2, 1, N)
+        ix4.engine.close()
+        del ix4
+        torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and sample_host is not None:
-        qs = q_dev[:args.cpu_sample_queries].cpu().numpy()
-        cpu, _ = cpu_reference_qps(args, sample_host, qs, steps=1, warmup=1)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 1 << 62
+        need = N * d * 4
+        path = f"/dev/shm/b2ip_bench_corpus_{os.getpid()}.f32"
+        if avail > need * 1.25 + (8 << 30):
+            try:
+                mm = np.memmap(path, dtype=np.float32, mode="w+", shape=(N, d))
+                for r0 in range(0, N, 1 << 20):
+                    m = min(1 << 20, N - r0)
+                    index.engine.export_rows(r0, m, out=mm[r0:r0 + m])
+                mm.flush()
+                del mm
+                cpu = cpu_baseline_subprocess(args, path, "c5:1,c5:64" if args.workload == "c3" else "")
+            finally:
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
+        else:
+            cpu = {"error": f"host memory too small for the full corpus ({avail >> 30} GiB available, {need >> 30} GiB needed)"}
 
-    launches = int(sum_over_ranks(agg["launches"]))
-    # order-independent digest of the last step's results: identical at every N (the sharded
-    # search returns the single-GPU answer bit for bit), so the scaling runs check each other
-    checksum = {"ids_sum": int(I_last.sum().item()),
-                "ids_weighted": int((I_last * torch.arange(1, k + 1, device=dev)).sum().item() % (1 << 61)),
-                "scores_sum_f64": float(D_last.double().sum().item())}
+    # ---------------------------------------------------------------- the drop-in call: Indexer.search_knn
+    knn = None
+    exchange_desc = ("peer-direct (b2ip_search_exchange)" if world > 1 and getattr(index, "exchange_searches", 0) > 0
+                     else ("nccl all-gather + merge" if world > 1 else "none"))
+    if not args.no_search_knn:
+        q_half = q_host.astype(np.float16)            # the reference's default query dtype (model.half())
+        n_knn = max(1, min(3, args.steps))
+
+        def time_knn(ix):
+            ix.search_knn(q_half[:4096], k)                                  # warm the buffers
+            ts = []
+            for _ in range(n_knn):
+                t0 = time.perf_counter()
+                res = ix.search_knn(q_half, k)
+                ts.append(time.perf_counter() - t0)
+            # the drop-in's answer for the first rows == the engine's own answer for the same
+            # (float16-valued) queries, ids as strings
+            _, I8 = ix.index.search(q_half[:8].astype(np.float32), k)
+            I8 = I8.cpu().numpy() if hasattr(I8, "cpu") else I8
+            same = all([int(x) for x in res[j][0]] == I8[j].tolist() for j in range(8)) and len(res) == nq
+            return min(ts), sum(ts) / len(ts), same
+
+        if world == 1:
+            # the drop-in object around the engine already in HBM
+            ixr = Indexer.from_engine(index.engine, [str(i) for i in range(N)])
+            best, mean, ok = time_knn(ixr)
+            knn = {"value": nq / best, "unit": UNIT, "ms_per_call": best * 1e3, "ms_per_call_mean": mean * 1e3,
+                   "calls": n_knn, "devices": 1, "vs_device_step": best * 1e3 / ms_per_step,
+                   "queries": "pageable float16 numpy [nq,768]", "returns": "list of (list[str] * k, float32[k])",
+                   "matches_engine_result": bool(ok),
+                   "call": "Indexer.search_knn (b2ip/indexer.py <- reference src/index.py:34-46)"}
+        else:
+            # an unmodified reference driver is ONE process: it reaches the N GPUs through
+            # Indexer(device="all").  The per-rank shards are dropped first, rank 0 rebuilds the
+            # index through the drop-in's own index_data and times search_knn; the others wait.
+            index.engine.close()
+            del index
+            torch.cuda.empty_cache()
+            D.barrier()
+            if rank == 0:
+                ixr = Indexer(d, 0, 8, device=list(range(world)), store="f32")
+                ixr.index.reserve(N)
+                for g0, rows in gen_rows(torch, 0, N, d, 1234, dev):
+                    ixr.index.add(rows)
+                ixr.index_id_to_db_id = [str(i) for i in range(N)]
+                best, mean, ok = time_knn(ixr)
+                st = ixr.index.stats()
+                knn = {"value": nq / best, "unit": UNIT, "ms_per_call": best * 1e3, "ms_per_call_mean": mean * 1e3,
+                       "calls": n_knn, "devices": world, "vs_device_step": best * 1e3 / ms_per_step,
+                       "queries": "pageable float16 numpy [nq,768]", "returns": "list of (list[str] * k, float32[k])",
+                       "matches_engine_result": bool(ok),
+                       "gpu_ms_last_chunk": st.get("total_ms"),
+                       "call": "Indexer(device='all').search_knn: one process, MultiGpuEngine over all GPUs "
+                               "(B2IP_DEVICES=all for an unmodified passage_retrieval.py)"}
+                ixr.index.close()
+            D.barrier()
+
     if rank == 0:
         line = {
-            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(N, k, d), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
             "dtype": f"{args.store if args.store != 'f32' else (args.shadow or 'bf16')} coarse / f32 rescore",
             "data": "synthetic", "config": workload_config(args, world),
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "result_checksum": checksum,
+            "e2e": e2e, "e2e_search_knn": knn, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "parity_probe": probe, "result_checksum": checksum, "secondary": secondary,
             "detail": {"ingest_s": t_ing, "rows_per_gpu": hi - lo,
-                       "candidates_per_query_per_step": agg["candidates"] / max(1, args.steps) / nq,
-                       "rescored_per_query_per_step": agg["rescored"] / max(1, args.steps) / nq,
-                       "fallback_queries": agg["fallback"], "slabs_per_step": agg["slabs"] / max(1, args.steps),
-                       "rank0_ms_per_step": {"coarse": agg["coarse_ms"] / max(1, args.steps),
-                                             "refresh": agg["refresh_ms"] / max(1, args.steps),
-                                             "finalize": agg["finalize_ms"] / max(1, args.steps),
-                                             "search_device_total": agg["device_ms"] / max(1, args.steps)},
-                       "exchange": ("peer-direct (b2ip_search_exchange)" if getattr(index, "exchange_searches", 0) > 0
-                                    else ("nccl all-gather + merge" if world > 1 else "none"))},
+                       "candidates_per_query_per_step": agg["candidates"] / args.steps / nq,
+                       "rescored_per_query_per_step": agg["rescored"] / args.steps / nq,
+                       "fallback_queries": int(agg["fallback"]), "slabs_per_step": agg["slabs"] / args.steps,
+                       "max_err_over_eps": agg["max_err_over_eps"], "bound_violations": int(agg["bound_violations"]),
+                       "rank0_ms_per_step": {"coarse": agg["coarse_ms"] / args.steps,
+                                             "refresh": agg["refresh_ms"] / args.steps,
+                                             "finalize": agg["finalize_ms"] / args.steps,
+                                             "search_device_total": agg["device_ms"] / args.steps},
+                       "exchange": exchange_desc},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -21,7 +21,7 @@ MAX_K = 2048
 # every symbol include/b2ip.h declares (tests check the .so exports all of them)
 SYMBOLS = (
     "b2ip_create", "b2ip_create_ex", "b2ip_destroy", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_ntotal",
-    "b2ip_dim", "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_exchange", "b2ip_merge_topk", "b2ip_merge_topk_strided", "b2ip_export_rows",
+    "b2ip_dim", "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_ex", "b2ip_search_exchange", "b2ip_enable_peer_access", "b2ip_merge_topk", "b2ip_merge_topk_strided", "b2ip_export_rows",
     "b2ip_copy_to_device", "b2ip_copy_to_host", "b2ip_stats", "b2ip_last_error", "b2ip_debug_coarse_scores", "b2ip_version",
 )
 
@@ -37,6 +37,7 @@ class Stats(ctypes.Structure):
         ("fallback_queries", ctypes.c_int64),
         ("slabs", ctypes.c_int32), ("query_batches", ctypes.c_int32),
         ("refresh_ms", ctypes.c_float), ("finalize_ms", ctypes.c_float),
+        ("max_err_over_eps", ctypes.c_double), ("bound_violations", ctypes.c_int64),
     ]
 
     def as_dict(self) -> dict:
@@ -44,12 +45,16 @@ class Stats(ctypes.Structure):
 
 
 MAX_PEERS = 8
+GATHER_ALL, GATHER_OWNER = 0, 1
+XF_WORDS = 4              # uint32 flag words per publishing rank (csrc/select_kernels.cuh)
 
 
 class Exchange(ctypes.Structure):
     """b2ip_exchange_t (include/b2ip.h): peer-mapped gather buffers and flag arrays of one parity."""
     _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("slot_bytes", ctypes.c_int64),
-                ("gather", ctypes.c_void_p * MAX_PEERS), ("flags", ctypes.c_void_p * MAX_PEERS)]
+                ("gather", ctypes.c_void_p * MAX_PEERS), ("flags", ctypes.c_void_p * MAX_PEERS),
+                ("gthr", ctypes.c_void_p * MAX_PEERS), ("thr_stride", ctypes.c_int64),
+                ("gather_mode", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class B2ipError(RuntimeError):
@@ -87,8 +92,10 @@ def load() -> ctypes.CDLL:
     lib.b2ip_set_row_offset.argtypes = [vp, i64]
     lib.b2ip_set_row_segments.argtypes = [vp, i32, vp, vp]
     lib.b2ip_search.argtypes = [vp, i64, vp, i32, vp, vp, i32, i32]
+    lib.b2ip_search_ex.argtypes = [vp, i64, vp, i32, i32, vp, vp, i32, i32]
     lib.b2ip_search_exchange.argtypes = [vp, i64, vp, i32, ctypes.POINTER(Exchange), ctypes.c_uint32, vp, vp,
                                          ctypes.POINTER(ctypes.c_int64)]
+    lib.b2ip_enable_peer_access.argtypes = [vp, i32]
     lib.b2ip_merge_topk.argtypes = [i32, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.b2ip_merge_topk_strided.argtypes = [i32, vp, i64, i32, i32, vp, vp, i64, i64, vp, vp]
     lib.b2ip_export_rows.argtypes = [vp, i64, i64, vp, i32]
@@ -100,12 +107,34 @@ def load() -> ctypes.CDLL:
     lib.b2ip_debug_coarse_scores.argtypes = [vp, i64, vp, i64, i64, vp]
     lib.b2ip_version.restype = ctypes.c_char_p
     for name in ("b2ip_create", "b2ip_create_ex", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_dim",
-                 "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_exchange", "b2ip_merge_topk", "b2ip_merge_topk_strided",
+                 "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_ex", "b2ip_search_exchange", "b2ip_enable_peer_access", "b2ip_merge_topk", "b2ip_merge_topk_strided",
                  "b2ip_export_rows", "b2ip_stats", "b2ip_debug_coarse_scores", "b2ip_copy_to_device",
                  "b2ip_copy_to_host"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib
+
+
+_hostmap = None
+
+
+def load_hostmap():
+    """The CPython extension csrc/hostmap.c (`map_ids`: the row -> external id loop of
+    reference src/index.py:44-45 in C).  Built next to libb2ip.so by `make -C csrc`."""
+    global _hostmap
+    if _hostmap is None:
+        import glob
+        import importlib.util
+        hits = sorted(glob.glob(os.path.join(_PKG_ROOT, "lib", "_b2ip_hostmap*.so")))
+        if not hits:
+            raise ImportError(
+                f"{os.path.join(_PKG_ROOT, 'lib')}/_b2ip_hostmap*.so not found: build the native "
+                "pieces first (make -C czech-contriever_b200/csrc)")
+        spec = importlib.util.spec_from_file_location("_b2ip_hostmap", hits[-1])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _hostmap = mod
+    return _hostmap
 
 
 def check(rc: int, handle=None) -> None:

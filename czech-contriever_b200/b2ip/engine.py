@@ -116,8 +116,10 @@ class Engine:
         check(self._lib.b2ip_add(self._h, rows.shape[0], ctypes.c_void_p(rows.ctypes.data), dt,
                                  MEM_HOST), self._h)
 
-    def export_rows(self, row0: int, n: int) -> np.ndarray:
-        out = np.empty((n, self.d), dtype=np.float32)
+    def export_rows(self, row0: int, n: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((n, self.d), dtype=np.float32)
+        assert out.dtype == np.float32 and out.shape == (n, self.d) and out.flags["C_CONTIGUOUS"]
         check(self._lib.b2ip_export_rows(self._h, int(row0), int(n), ctypes.c_void_p(out.ctypes.data),
                                          MEM_HOST), self._h)
         return out
@@ -131,7 +133,9 @@ class Engine:
         if _is_torch(queries):
             import torch
             assert queries.is_cuda and queries.device.index == self.device
-            q = queries.float().contiguous()
+            # float16 queries cross the ABI as they are and are widened by the library (exact)
+            q = queries.contiguous() if queries.dtype in (torch.float16, torch.float32) \
+                else queries.float().contiguous()
             assert q.dim() == 2 and q.shape[1] == self.d, tuple(q.shape)
             nq = q.shape[0]
             if out is None:
@@ -140,11 +144,15 @@ class Engine:
             else:
                 D, I = out
             torch.cuda.current_stream(self.device).synchronize()
-            check(self._lib.b2ip_search(self._h, nq, ctypes.c_void_p(q.data_ptr()), k,
-                                        ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
-                                        m, MEM_DEVICE), self._h)
+            check(self._lib.b2ip_search_ex(self._h, nq, ctypes.c_void_p(q.data_ptr()),
+                                           B2IP_F16 if q.dtype == torch.float16 else B2IP_F32, k,
+                                           ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                           m, MEM_DEVICE), self._h)
             return D, I
-        q = np.ascontiguousarray(np.asarray(queries), dtype=np.float32)
+        q = np.asarray(queries)
+        if q.dtype not in (np.float16, np.float32):
+            q = q.astype(np.float32)
+        q = np.ascontiguousarray(q)
         if q.ndim != 2 or q.shape[1] != self.d:
             raise ValueError(f"expected [nq,{self.d}] queries, got {q.shape}")
         nq = q.shape[0]
@@ -153,22 +161,33 @@ class Engine:
             I = np.empty((nq, k), dtype=np.int64)
         else:
             D, I = out
-        check(self._lib.b2ip_search(self._h, nq, ctypes.c_void_p(q.ctypes.data), k,
-                                    ctypes.c_void_p(D.ctypes.data), ctypes.c_void_p(I.ctypes.data),
-                                    m, MEM_HOST), self._h)
+        check(self._lib.b2ip_search_ex(self._h, nq, ctypes.c_void_p(q.ctypes.data),
+                                       B2IP_F16 if q.dtype == np.float16 else B2IP_F32, k,
+                                       ctypes.c_void_p(D.ctypes.data), ctypes.c_void_p(I.ctypes.data),
+                                       m, MEM_HOST), self._h)
         return D, I
+
+    def enable_peer_access(self, peer_device: int) -> None:
+        """Kernels of this engine's GPU may store into memory of `peer_device` (same process)."""
+        check(self._lib.b2ip_enable_peer_access(self._h, int(peer_device)), self._h)
 
     def search_exchange(self, queries, k: int, ex, seq: int):
         """Local search + peer-direct exchange + merge in one call (b2ip_search_exchange).
         `ex`: _lib.Exchange of this parity.  Returns (D, I, status): the GLOBAL top-k on this
-        rank's device and the number of overflowed queries over all ranks (non-zero: repeat the
-        search through the all-gather path)."""
+        rank's device -- of every query (ex.gather_mode == GATHER_ALL) or of the queries this
+        rank owns, `shard_bounds(nq, world, rank)`, compactly (GATHER_OWNER) -- and the number of
+        overflowed queries over all ranks (non-zero: repeat the search through the all-gather path)."""
         import torch
         q = queries.float().contiguous()
         assert q.is_cuda and q.device.index == self.device and q.dim() == 2 and q.shape[1] == self.d
         nq, k = q.shape[0], int(k)
-        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        n_out = nq
+        if ex.gather_mode == _lib.GATHER_OWNER:
+            per = -(-nq // ex.world)
+            lo = min(ex.rank * per, nq)
+            n_out = min(lo + per, nq) - lo
+        D = torch.empty((n_out, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((n_out, k), dtype=torch.int64, device=q.device)
         status = ctypes.c_int64(0)
         torch.cuda.current_stream(self.device).synchronize()
         check(self._lib.b2ip_search_exchange(self._h, nq, ctypes.c_void_p(q.data_ptr()), k, ctypes.byref(ex),

@@ -8,9 +8,10 @@ deliberate:
   * `n_subquantizers > 0` (faiss.IndexPQ, src/index.py:18-19) raises: approximate search is
     not on this path and there is no CPU fallback.
   * `index_batch_size` is a hint: queries are independent, the engine batches them itself.
-  * the id mapping of src/index.py:44 (nq*k Python str() calls) is done once per id at
-    first use and then by one fancy-index -- same strings, same `[-1]` = last-id quirk
-    for the -1 padding the reference has when the index holds fewer than k rows.
+  * the id mapping of src/index.py:44 (nq*k Python str() calls) runs in C (csrc/hostmap.c),
+    pipelined behind the GPU search chunk by chunk -- same strings, same `[-1]` = last-id
+    quirk for the -1 padding the reference has when the index holds fewer than k rows.
+  * `search_knn` also takes a torch CUDA tensor (the query encoder's output, left on the GPU).
   * storage (`store=` / env B2IP_STORE, default "auto"): the reference widens whatever it is
     given to float32 (src/index.py:27).  Its default pipeline hands in float16 shards
     (generate_passage_embeddings.py:75-76); widening is exact, so "auto" keeps such rows as
@@ -27,7 +28,9 @@ from typing import List, Tuple
 
 import numpy as np
 
-from .engine import Engine
+from ._lib import load_hostmap
+from .engine import Engine, _is_torch
+from .ingest import prefetch
 from .multi import MultiGpuEngine
 from .faiss_io import stream_flat_ip_rows, write_flat_ip
 
@@ -54,7 +57,19 @@ class Indexer(object):
         self.store = store
         self.index = self._new_engine(vector_sz, "f16" if store == "f16" else "f32")
         self.index_id_to_db_id = []
-        self._str_ids = None
+        self.knn_chunk = 16384        # queries per pipelined search_knn chunk (env B2IP_KNN_CHUNK)
+
+    @classmethod
+    def from_engine(cls, engine, ids=None, store=None) -> "Indexer":
+        """The drop-in object around an engine that already holds the rows (e.g. one built
+        from device tensors): `ids` become `index_id_to_db_id`."""
+        self = cls.__new__(cls)
+        self.vector_sz, self.store = engine.d, store or engine.store
+        self.device = getattr(engine, "devices", None) or engine.device
+        self.index = engine
+        self.index_id_to_db_id = list(ids) if ids is not None else []
+        self.knn_chunk = 16384
+        return self
 
     def _new_engine(self, d, store):
         if self.device == "all":
@@ -94,17 +109,55 @@ class Indexer(object):
         print(f'Total data indexed {len(self.index_id_to_db_id)}')
 
     def search_knn(self, query_vectors: np.array, top_docs: int, index_batch_size: int = 2048) -> List[Tuple[List[object], List[float]]]:
-        query_vectors = np.asarray(query_vectors).astype('float32')
-        if len(query_vectors) == 0:
+        """reference src/index.py:34-46, same return value: nq tuples (list of k external ids as
+        `str`, float32 score row), rows score-descending.  `query_vectors` may be a numpy array
+        (float16 / float32 are handed to the library as they are -- float16 is widened on the
+        GPU, which is what `astype('float32')` computes -- anything else goes through float32)
+        or a torch tensor; a CUDA tensor is searched where it lies (no host round trip of the
+        queries: SURVEY 8f N4, the encoder's output can stay on the device).
+
+        The queries are searched in chunks on a background thread while this thread maps the
+        previous chunk's rows to external ids (csrc/hostmap.c: the reference's nq*k str() loop
+        in C), so the host half of the call hides behind the GPU half."""
+        q = query_vectors
+        on_device = False
+        if _is_torch(q):
+            q = q.detach()
+            if q.is_cuda:
+                on_device = True
+            else:
+                q = q.numpy()
+        if not on_device:
+            q = np.asarray(q)
+            if q.dtype not in (np.float16, np.float32):
+                q = q.astype('float32')
+        nq = len(q)
+        if nq == 0:
             return []
-        scores, indexes = self.index.search(query_vectors, top_docs)
-        # convert to external ids
-        if self._str_ids is None or len(self._str_ids) != len(self.index_id_to_db_id):
-            self._str_ids = np.array([str(i) for i in self.index_id_to_db_id], dtype=object)
-        if len(self._str_ids) == 0:
-            raise IndexError('list index out of range')   # what the reference's [-1] lookup raises
-        db_ids = self._str_ids[indexes].tolist()
-        return [(db_ids[i], scores[i]) for i in range(len(db_ids))]
+        ids = self.index_id_to_db_id
+        if not isinstance(ids, list):
+            ids = list(ids)
+        map_ids = load_hostmap().map_ids
+        chunk = max(1, int(os.environ.get("B2IP_KNN_CHUNK", self.knn_chunk)))
+        index = self.index
+
+        def searches():
+            for s in range(0, nq, chunk):
+                D, I = index.search(q[s:s + chunk], top_docs)
+                if on_device:
+                    Dn = np.empty(tuple(D.shape), np.float32)
+                    In = np.empty(tuple(I.shape), np.int64)
+                    index.download(D.contiguous(), Dn)
+                    index.download(I.contiguous(), In)
+                    D, I = Dn, In
+                yield D, I
+
+        result = []
+        # convert to external ids (negative rows index from the end, like the reference's
+        # `index_id_to_db_id[-1]` for faiss's -1 padding; an empty id list raises IndexError)
+        for scores, indexes in prefetch(searches(), depth=2):
+            result.extend(map_ids(ids, indexes, indexes.shape[0], indexes.shape[1], list(scores)))
+        return result
 
     def serialize(self, dir_path):
         index_file = os.path.join(dir_path, 'index.faiss')
@@ -132,10 +185,8 @@ class Indexer(object):
 
         with open(meta_file, "rb") as reader:
             self.index_id_to_db_id = pickle.load(reader)
-        self._str_ids = None
         assert len(
             self.index_id_to_db_id) == self.index.ntotal, 'Deserialized index_id_to_db_id should match faiss index size'
 
     def _update_id_mapping(self, db_ids: List):
         self.index_id_to_db_id.extend(db_ids)
-        self._str_ids = None

@@ -4,17 +4,23 @@ The reference runs its retrieval in a single process (passage_retrieval.py never
 torch.distributed), so a drop-in `Indexer` cannot assume `torchrun`.  This class
 gives that single process every GPU of the box: one `Engine` (= one C-ABI handle, one row
 shard) per device, host threads that run the per-device searches concurrently (the ctypes call
-releases the GIL), peer-to-peer copies of the per-shard [nq,k] results to the first device
-and the same merge kernel (`b2ip_merge_topk_strided`) the NCCL path uses.  Same surface as
+releases the GIL) and the SAME fused peer-direct exchange as the one-process-per-GPU path
+(`b2ip_search_exchange`: global threshold round, every finalize kernel stores its block into
+the owner GPU's gather buffer over NVLink, each GPU merges the queries it owns) -- between
+handles of one process the peer buffers are plain device pointers.  Each GPU then copies its
+slice of the result to the host on its own copy engine.  Without P2P between the devices the
+per-shard results are copied to the first device and merged there (`b2ip_merge_topk_strided`).  Same surface as
 `Engine` (add / search / ntotal / export_rows / reserve / stats / close), same results: the
 merge keeps score-descending order and the lower GLOBAL row among equal scores.
 
-Every `add` splits its rows contiguously over the devices, so shards stay balanced however
-the caller chunks its data; a per-engine segment table maps local rows back to global ids.
+Every `add` cuts its rows into consecutive slices that level the shards' running totals, so
+shards stay balanced however the caller chunks its data; a per-engine segment table maps
+local rows back to global ids.
 """
 from __future__ import annotations
 
 import bisect
+import os
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Sequence, Tuple
 
@@ -77,6 +83,20 @@ class SegmentMap:
                 yield ls + (a - gs), a, b - a
 
 
+def level_split(totals: Sequence[int], n: int) -> List[int]:
+    """How many of n new rows each shard takes (consecutive slices, in shard order) so that the
+    running totals stay level: shard g aims at its share of the new grand total; totals never
+    differ by more than one row once they were level."""
+    G, N, left, out = len(totals), sum(totals) + n, n, []
+    for g in range(G):
+        target = N * (g + 1) // G - N * g // G
+        take = min(max(target - totals[g], 0), left)
+        out.append(take)
+        left -= take
+    assert left == 0, (totals, n, out)
+    return out
+
+
 class MultiGpuEngine:
     def __init__(self, d: int, devices: Optional[Sequence[int]] = None, store: str = "f32",
                  shadow: Optional[str] = None):
@@ -93,6 +113,9 @@ class MultiGpuEngine:
         self._n = 0
         self._pool = ThreadPoolExecutor(max_workers=len(devices))
         self._last_stats: List[dict] = []
+        self._x_ok = None if os.environ.get("B2IP_PEER_EXCHANGE", "1") != "0" else False
+        self._x_ex, self._x_bufs, self._x_slot, self._x_thr_cap, self._x_seq = None, None, 0, 0, 0
+        self.exchange_searches = 0
 
     # -- lifetime / configuration ----------------------------------------------------
     def close(self) -> None:
@@ -127,16 +150,18 @@ class MultiGpuEngine:
 
     # -- data ------------------------------------------------------------------------
     def add(self, rows) -> None:
-        """Rows get global ids ntotal .. ntotal+n-1; slice g of the chunk goes to device g."""
+        """Rows get global ids ntotal .. ntotal+n-1.  The chunk is cut into consecutive slices,
+        one per device, sized to LEVEL the shards' running totals (a remainder or a chunk smaller
+        than the number of devices goes to the least-filled shards, not always to device 0)."""
         n = int(rows.shape[0])
-        G = len(self.engines)
-        per = -(-n // G) if n else 0
-        jobs = []
-        for g, e in enumerate(self.engines):
-            lo, hi = min(g * per, n), min((g + 1) * per, n)
+        jobs, lo = [], 0
+        for g, take in enumerate(level_split([m.n_local for m in self.maps], n)):
+            hi = lo + take
             if hi > lo:
                 self.maps[g].append(self._n + lo, hi - lo)
                 jobs.append(self._pool.submit(self._add_one, g, rows[lo:hi]))
+            lo = hi
+        assert lo == n
         for j in jobs:
             j.result()
         for g, e in enumerate(self.engines):
@@ -168,49 +193,144 @@ class MultiGpuEngine:
             torch.cuda.current_stream(dev).synchronize()
         return D, I, st
 
+    FLAG_BYTES = 256
+
+    def _exchange(self, nq: int, k: int):
+        """Per-device gather / threshold / flag buffers of the fused exchange (two parities) and
+        the b2ip_exchange_t of every device; None when the devices cannot reach each other."""
+        if self._x_ok is False:
+            return None
+        need = (nq * k * 12 + 15) // 16 * 16
+        if self._x_ex is not None and need <= self._x_slot and nq <= self._x_thr_cap:
+            return self._x_ex
+        from ._lib import GATHER_OWNER, B2ipError, Exchange
+        torch = self._torch
+        G = len(self.engines)
+        if self._x_ok is None:
+            try:
+                for a in range(G):
+                    for b in range(G):
+                        self.engines[a].enable_peer_access(self.devices[b])
+                self._x_ok = True
+            except B2ipError:
+                self._x_ok = False
+                return None
+        slot = max(1 << 16, (need + need // 4 + 65535) // 65536 * 65536, self._x_slot)
+        thr_cap = max((nq + nq // 4 + 1023) // 1024 * 1024, self._x_thr_cap)
+        thr_bytes = G * thr_cap * 4
+        total = 2 * G * slot + 2 * thr_bytes + 2 * self.FLAG_BYTES
+        for dev in self.devices:
+            torch.cuda.synchronize(dev)
+        bufs = [torch.zeros(total, dtype=torch.uint8, device=torch.device("cuda", dev)) for dev in self.devices]
+        for dev in self.devices:
+            torch.cuda.synchronize(dev)
+        ptrs = [b.data_ptr() for b in bufs]
+        exs = []
+        for g in range(G):
+            pair = []
+            for parity in (0, 1):
+                ex = Exchange()
+                ex.world, ex.rank, ex.slot_bytes = G, g, slot
+                ex.thr_stride, ex.gather_mode = thr_cap, GATHER_OWNER
+                for p in range(G):
+                    ex.gather[p] = ptrs[p] + parity * G * slot
+                    ex.gthr[p] = ptrs[p] + 2 * G * slot + parity * thr_bytes
+                    ex.flags[p] = ptrs[p] + 2 * G * slot + 2 * thr_bytes + parity * self.FLAG_BYTES
+                pair.append(ex)
+            exs.append(pair)
+        self._x_bufs, self._x_slot, self._x_thr_cap, self._x_ex, self._x_seq = bufs, slot, thr_cap, exs, 0
+        return exs
+
+    def _search_exchange_one(self, g: int, q_dev0, k: int, ex, seq: int, host_out, lo: int, hi: int):
+        """Device g: fan-in of the queries, search + exchange + merge of the queries it owns, and
+        (host output) the D2H of that slice on this device's copy engine."""
+        torch = self._torch
+        dev = torch.device("cuda", self.devices[g])
+        with torch.cuda.device(dev):
+            q = q_dev0 if q_dev0.device == dev else q_dev0.to(dev)
+            D, I, status = self.engines[g].search_exchange(q, k, ex, seq)
+            st = self.engines[g].stats()
+            if status == 0 and host_out is not None and hi > lo:
+                self.engines[g].download(D, host_out[0][lo:hi])
+                self.engines[g].download(I, host_out[1][lo:hi])
+        return D, I, st, status
+
     def search(self, queries, k: int, mode: str = "auto", out=None):
         """numpy in -> numpy out, torch CUDA tensor in -> tensors on the first device."""
         torch = self._torch
         k = int(k)
+        G = len(self.engines)
+        dev0 = torch.device("cuda", self.devices[0])
         is_t = type(queries).__module__.startswith("torch")
         if is_t:
-            q_dev0, q_host = queries.float().contiguous(), None
+            q_dev0 = queries if queries.dtype in (torch.float16, torch.float32) else queries.float()
+            q_dev0 = q_dev0.contiguous()
             torch.cuda.current_stream(q_dev0.device).synchronize()
             nq = q_dev0.shape[0]
         else:
-            q_host = np.ascontiguousarray(np.asarray(queries), dtype=np.float32)
+            q_host = np.asarray(queries)
+            if q_host.dtype not in (np.float16, np.float32):
+                q_host = q_host.astype(np.float32)
+            q_host = np.ascontiguousarray(q_host)
             if q_host.ndim != 2 or q_host.shape[1] != self.d:
                 raise ValueError(f"expected [nq,{self.d}] queries, got {q_host.shape}")
             nq = q_host.shape[0]
-            with torch.cuda.device(self.devices[0]):
-                # one staged upload (pinned double buffering inside the library), then P2P fan-out
-                q_dev0 = torch.empty((nq, self.d), dtype=torch.float32,
-                                     device=torch.device("cuda", self.devices[0]))
+            with torch.cuda.device(dev0):
+                # one staged upload (pinned double buffering inside the library), then P2P fan-out;
+                # float16 queries stay float16 until they are on the device
+                q_dev0 = torch.empty((nq, self.d), device=dev0,
+                                     dtype=torch.float16 if q_host.dtype == np.float16 else torch.float32)
                 if nq:
                     self.engines[0].upload(q_dev0, q_host)
-        dev0 = torch.device("cuda", self.devices[0])
+        host_out = None
+        if not is_t:
+            host_out = out if out is not None else (np.empty((nq, k), np.float32), np.empty((nq, k), np.int64))
         if nq == 0:
-            D = torch.empty((0, k), dtype=torch.float32, device=dev0)
-            I = torch.empty((0, k), dtype=torch.int64, device=dev0)
-        else:
-            parts = [self._pool.submit(self._search_one, g, q_dev0, k, mode)
-                     for g in range(len(self.engines))]
+            if is_t:
+                return (torch.empty((0, k), dtype=torch.float32, device=dev0),
+                        torch.empty((0, k), dtype=torch.int64, device=dev0))
+            return host_out
+        D = I = None
+        ex = self._exchange(nq, k) if (G > 1 and mode != "exact") else None
+        if ex is not None:
+            self._x_seq += 1
+            per = -(-nq // G)
+            spans = [(min(g * per, nq), min(min(g * per, nq) + per, nq)) for g in range(G)]
+            parts = [self._pool.submit(self._search_exchange_one, g, q_dev0, k, ex[g][self._x_seq & 1],
+                                       self._x_seq, host_out, *spans[g]) for g in range(G)]
             res = [p.result() for p in parts]
             self._last_stats = [r[2] for r in res]
-            with torch.cuda.device(dev0):
-                if len(res) == 1:
-                    D, I = res[0][0], res[0][1]
-                else:
-                    gD = torch.stack([r[0].to(dev0) for r in res])
-                    gI = torch.stack([r[1].to(dev0) for r in res])
-                    D, I = merge_topk(gD, gI, k)
+            if all(r[3] == 0 for r in res):
+                self.exchange_searches += 1
+                if not is_t:
+                    return host_out
+                with torch.cuda.device(dev0):
+                    return (torch.cat([r[0].to(dev0) for r in res]), torch.cat([r[1].to(dev0) for r in res]))
+            # a candidate list overflowed somewhere (same status on every device): repeat below
+        parts = [self._pool.submit(self._search_one, g, q_dev0, k, mode) for g in range(G)]
+        res = [p.result() for p in parts]
+        self._last_stats = [r[2] for r in res]
+        with torch.cuda.device(dev0):
+            if len(res) == 1:
+                D, I = res[0][0], res[0][1]
+            else:
+                gD = torch.empty((G, nq, k), dtype=torch.float32, device=dev0)
+                gI = torch.empty((G, nq, k), dtype=torch.int64, device=dev0)
+                for g, r in enumerate(res):                 # one P2P copy per shard, straight into place
+                    gD[g].copy_(r[0])
+                    gI[g].copy_(r[1])
+                D, I = merge_topk(gD, gI, k)
         if is_t:
             return D, I
-        Dn, In = out if out is not None else (np.empty((nq, k), np.float32), np.empty((nq, k), np.int64))
-        if nq:
-            self.engines[0].download(D.contiguous(), Dn)
-            self.engines[0].download(I.contiguous(), In)
-        return Dn, In
+        self.engines[0].download(D.contiguous(), host_out[0])
+        self.engines[0].download(I.contiguous(), host_out[1])
+        return host_out
+
+    def download(self, src, dst: np.ndarray) -> None:
+        """dst (host array) <- src (CUDA tensor on any of this engine's devices)."""
+        g = self.devices.index(src.device.index)
+        with self._torch.cuda.device(src.device):
+            self.engines[g].download(src, dst)
 
     def stats(self) -> dict:
         """Per-device stats of the last search, plus sums of the additive counters."""

@@ -27,7 +27,7 @@ def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 class ShardedIndex:
-    FLAG_BYTES = 256          # per parity: uint32[2 * world] flags, padded
+    FLAG_BYTES = 256          # per parity: uint32[4 * world] flags (XF_WORDS per rank), padded
 
     def __init__(self, d: int, device: Optional[int] = None, engine=None, group=None,
                  merge_fn: Optional[Callable] = None, store: str = "f32",
@@ -58,8 +58,11 @@ class ShardedIndex:
             peer_exchange = os.environ.get("B2IP_PEER_EXCHANGE", "1") != "0"
         self.peer_exchange = bool(peer_exchange) and self.world > 1 and self.world <= 8 \
             and self._engine_writes_in_place()
-        self._x_buf = None        # symmetric buffer [2 parities x world slots | 2 flag arrays]
+        # global threshold round of the exchange (include/b2ip.h): each rank rescores ~k/world rows
+        self.global_threshold = os.environ.get("B2IP_GLOBAL_THRESHOLD", "1") != "0"
+        self._x_buf = None        # symmetric buffer [gather slots | threshold rows | flag arrays] x 2 parities
         self._x_slot = 0
+        self._x_thr_cap = 0
         self._x_ex = None
         self._x_seq = 0
         self.exchange_searches = 0
@@ -130,36 +133,103 @@ class ShardedIndex:
         Returns the global (scores [nq,k], rows [nq,k]) on every rank."""
         if self.world == 1:
             return self.search_local(queries, k, mode)
-        if self.peer_exchange and mode != "exact" and int(queries.shape[0]) > 0:
+        D, I, _ = self._search_exchange(queries, k, mode, owner=False)
+        return D, I
+
+    def search_owned(self, queries, k: int, mode: str = "auto"):
+        """The same search with the result PARTITIONED over the ranks: every rank gets the global
+        top-k of the contiguous slice of queries it owns, `shard_bounds(nq, world, rank)`.
+        Returns (scores [q_hi-q_lo,k], rows [q_hi-q_lo,k], (q_lo, q_hi)).  This is the scalable
+        form of the exchange: a rank's block for a query crosses NVLink once (to the owner), each
+        query is merged once, and a consumer on the host reads 1/world of the result from every
+        GPU's copy engine in parallel."""
+        nq = int(queries.shape[0])
+        lo, hi = shard_bounds(nq, self.world, self.rank)
+        if self.world == 1:
+            D, I = self.search_local(queries, k, mode)
+            return D, I, (lo, hi)
+        return self._search_exchange(queries, k, mode, owner=True)
+
+    def _search_exchange(self, queries, k: int, mode: str, owner: bool):
+        nq = int(queries.shape[0])
+        lo, hi = shard_bounds(nq, self.world, self.rank)
+        if self.peer_exchange and mode != "exact" and nq > 0:
             try:
-                ex = self._exchange_buffers(int(queries.shape[0]), int(k))
+                ex = self._exchange_buffers(nq, int(k))
             except Exception as e:  # noqa: BLE001 - no symmetric memory on this box (same on every rank)
                 import warnings
                 warnings.warn(f"peer-direct exchange unavailable ({e!r}); using the NCCL all-gather path")
                 self.peer_exchange = False
-                return self._search_allgather(queries, k, mode)
-            self._x_seq += 1
-            D, I, status = self.engine.search_exchange(queries, k, ex[self._x_seq & 1], self._x_seq)
-            if status == 0:
-                self.exchange_searches += 1
-                return D, I
-            # some rank overflowed a candidate list (same status everywhere): all ranks repeat
-            # the search below, where the exact fallback runs before the exchange
-        return self._search_allgather(queries, k, mode)
+                ex = None
+            if ex is not None:
+                self._x_seq += 1
+                D, I, status = self.engine.search_exchange(
+                    queries, k, ex[1 if owner else 0][self._x_seq & 1], self._x_seq)
+                if status == 0:
+                    self.exchange_searches += 1
+                    return D, I, (lo, hi)
+                # some rank overflowed a candidate list (same status everywhere): all ranks repeat
+                # the search below, where the exact fallback runs before the exchange
+        D, I = self._search_allgather(queries, k, mode)
+        if owner:
+            return D[lo:hi].contiguous(), I[lo:hi].contiguous(), (lo, hi)
+        return D, I, (lo, hi)
+
+    def search_host(self, queries, k: int, out=None, mode: str = "auto"):
+        """Host buffers in and out (SPMD: every rank passes the same numpy queries [nq,d],
+        float16 or float32).  The queries go up through the engine's pinned staging, the global
+        top-k is computed as in `search`, and this rank downloads the contiguous slice of queries
+        it owns -- `shard_bounds(nq, world, rank)` -- into `out` = (D [nq,k] float32, I [nq,k]
+        int64).  With `out` backed by memory the ranks share (e.g. np.memmap of one /dev/shm
+        file) the union of the slices is the whole answer and the D2H runs on every GPU's copy
+        engine at once.  Returns (D, I, (q_lo, q_hi))."""
+        import numpy as np
+        torch = self._torch
+        q = np.asarray(queries)
+        if q.dtype not in (np.float16, np.float32):
+            q = q.astype(np.float32)
+        q = np.ascontiguousarray(q)
+        nq, k = int(q.shape[0]), int(k)
+        dev = torch.device("cuda", self.engine.device)
+        if out is None:
+            out = (np.empty((nq, k), dtype=np.float32), np.empty((nq, k), dtype=np.int64))
+        lo, hi = shard_bounds(nq, self.world, self.rank)
+        if nq == 0:
+            return out[0], out[1], (lo, hi)
+        tq = torch.empty((nq, self.d), dtype=torch.float16 if q.dtype == np.float16 else torch.float32, device=dev)
+        if self.world > 1 and nq >= 64 * self.world:
+            # every rank uploads the slice of queries it owns, NVLink all-gathers them
+            per = -(-nq // self.world)
+            pad = torch.empty((self.world * per, self.d), dtype=tq.dtype, device=dev)
+            if hi > lo:
+                self.engine.upload(pad[lo:hi], q[lo:hi])
+            self._dist.all_gather_into_tensor(pad, pad[self.rank * per:(self.rank + 1) * per], group=self.group)
+            tq = pad[:nq]
+        else:
+            self.engine.upload(tq, q)
+        D, I, _ = self.search_owned(tq, k, mode)
+        if hi > lo:
+            self.engine.download(D, out[0][lo:hi])
+            self.engine.download(I, out[1][lo:hi])
+        return out[0], out[1], (lo, hi)
 
     # -- peer-direct exchange --------------------------------------------------------
     def _exchange_buffers(self, nq: int, k: int):
-        """Symmetric (peer-mapped) gather buffers + flag arrays, two parities; grown collectively."""
+        """Symmetric (peer-mapped) memory of the exchange, two parities, grown collectively:
+        [2 x world gather slots | 2 x world x thr_cap floats (global threshold) | 2 flag arrays].
+        Returns ex[owner][parity] (_lib.Exchange; owner = 0: every rank gets everything, 1: owner mode)."""
         need = (nq * k * 12 + 15) // 16 * 16
-        if self._x_ex is not None and need <= self._x_slot:
+        if self._x_ex is not None and need <= self._x_slot and nq <= self._x_thr_cap:
             return self._x_ex
         import torch.distributed._symmetric_memory as symm_mem
-        from ._lib import Exchange
+        from ._lib import GATHER_ALL, GATHER_OWNER, Exchange
         torch, dist = self._torch, self._dist
         dev = torch.device("cuda", self.engine.device)
         # 25 % headroom (fewer collective re-allocations as nq*k creeps up), 64 KiB granules
-        slot = max(1 << 16, (need + need // 4 + 65535) // 65536 * 65536)
-        total = 2 * self.world * slot + 2 * self.FLAG_BYTES
+        slot = max(1 << 16, (need + need // 4 + 65535) // 65536 * 65536, self._x_slot)
+        thr_cap = max((nq + nq // 4 + 1023) // 1024 * 1024, self._x_thr_cap)
+        thr_bytes = self.world * thr_cap * 4
+        total = 2 * self.world * slot + 2 * thr_bytes + 2 * self.FLAG_BYTES
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)                 # nobody still uses the old buffers
         buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
@@ -169,14 +239,20 @@ class ShardedIndex:
         hdl.barrier()                                  # every rank's flags are zero before any write
         ptrs = list(hdl.buffer_ptrs)
         exs = []
-        for parity in (0, 1):
-            ex = Exchange()
-            ex.world, ex.rank, ex.slot_bytes = self.world, self.rank, slot
-            for p in range(self.world):
-                ex.gather[p] = ptrs[p] + parity * self.world * slot
-                ex.flags[p] = ptrs[p] + 2 * self.world * slot + parity * self.FLAG_BYTES
-            exs.append(ex)
-        self._x_buf, self._x_hdl, self._x_slot, self._x_ex, self._x_seq = buf, hdl, slot, exs, 0
+        for gather_mode in (GATHER_ALL, GATHER_OWNER):
+            pair = []
+            for parity in (0, 1):
+                ex = Exchange()
+                ex.world, ex.rank, ex.slot_bytes = self.world, self.rank, slot
+                ex.thr_stride, ex.gather_mode = thr_cap, gather_mode
+                for p in range(self.world):
+                    ex.gather[p] = ptrs[p] + parity * self.world * slot
+                    if self.global_threshold:
+                        ex.gthr[p] = ptrs[p] + 2 * self.world * slot + parity * thr_bytes
+                    ex.flags[p] = ptrs[p] + 2 * self.world * slot + 2 * thr_bytes + parity * self.FLAG_BYTES
+                pair.append(ex)
+            exs.append(pair)
+        self._x_buf, self._x_hdl, self._x_slot, self._x_thr_cap, self._x_ex, self._x_seq = buf, hdl, slot, thr_cap, exs, 0
         return exs
 
     # -- all-gather exchange -----------------------------------------------------------

@@ -73,7 +73,7 @@ struct b2ip_index_s {
     long long* h_gstats = nullptr;        // pinned host mirror
     PFN_encodeTiled encode = nullptr;
     // grow-only workspace
-    DevBuf q16, eps2, thr, cnt, kept, flags, cand, qstage, out_s, out_r, exact_scores, exact_misc,
+    DevBuf q16, eps2, thr, cnt, kept, flags, cand, qstage, qhalf, out_s, out_r, exact_scores, exact_misc,
         qlist, stage, seg_tab;
     int n_seg = 0;                        // row segments (b2ip_set_row_segments); 0 = row_offset
     std::vector<cudaEvent_t> ev_pool, ev_fin;
@@ -99,6 +99,9 @@ struct b2ip_index_s {
     long long ex_prior_overflow = 0;      // overflowed queries of earlier query batches of this search
     float* ex_out_s = nullptr;
     int64_t* ex_out_r = nullptr;
+    int extra_rank[MAX_PEERS - 1] = {};     // rank that owns extra_base[e]
+    bool ex_thr = false;                    // global threshold round active for this search
+    long long ex_timeout_ns = 600ll * 1000000000ll;   // B2IP_EXCHANGE_TIMEOUT_S
     size_t timing_events = 0;             // event triples of the last tensor search (read by b2ip_stats)
     bool timing_pending = false;
     const void* tmap_x_base = nullptr;
@@ -420,25 +423,48 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
 // After the last finalize of a search: tell every rank that this rank's [nq,k] block is in its
 // memory, then merge the world's blocks out of THIS rank's gather buffer as soon as all flags are
 // in.  Two launches behind finalize on the same stream -- no host round trip, no NCCL call.
-int enqueue_exchange(b2ip_handle h, int64_t nq, int k) {
-    const b2ip_exchange_t* ex = h->ex;
+PeerFlags peer_flags(const b2ip_exchange_t* ex) {
     PeerFlags pf{};
     pf.world = ex->world;
     pf.rank = ex->rank;
     for (int p = 0; p < ex->world; p++) pf.flags[p] = static_cast<unsigned int*>(ex->flags[p]);
-    exchange_signal_kernel<<<1, 32, 0, h->stream>>>(pf, h->ex_seq, h->gstats, h->ex_prior_overflow);
+    return pf;
+}
+
+// queries [q_lo, q_hi) of a search of nq queries belong to `rank` in owner mode
+void owner_range(const b2ip_exchange_t* ex, int64_t nq, int64_t* q_lo, int64_t* q_hi, int64_t* per) {
+    *per = (nq + ex->world - 1) / ex->world;
+    *q_lo = std::min<int64_t>(static_cast<int64_t>(ex->rank) * *per, nq);
+    *q_hi = std::min<int64_t>(*q_lo + *per, nq);
+}
+
+int enqueue_exchange(b2ip_handle h, int64_t nq, int k) {
+    const b2ip_exchange_t* ex = h->ex;
+    exchange_signal_kernel<<<1, 32, 0, h->stream>>>(peer_flags(ex), h->ex_seq, XF_RESULT, h->gstats,
+                                                    h->ex_prior_overflow);
+    h->stats.total_launches += 1;
     int P = 2;
     while (P < ex->world * k) P <<= 1;
     const size_t smem = static_cast<size_t>(P) * sizeof(unsigned long long);
     if (smem > 200 * 1024) return fail(h, B2IP_ERR_UNSUPPORTED, "exchange: world*k=%d too large", ex->world * k);
     CU_TRY(h, cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int64_t q_lo = 0, q_hi = nq, per = 0;
+    if (ex->gather_mode == B2IP_GATHER_OWNER) owner_range(ex, nq, &q_lo, &q_hi, &per);
     const char* mine = static_cast<const char*>(ex->gather[ex->rank]);
-    merge_topk_kernel<<<static_cast<unsigned int>(nq), SEL_THREADS, smem, h->stream>>>(
-        nq, k, ex->world, reinterpret_cast<const float*>(mine + static_cast<size_t>(nq) * k * 8),
-        reinterpret_cast<const long long*>(mine), ex->slot_bytes / 4, ex->slot_bytes / 8, h->ex_out_s,
-        reinterpret_cast<long long*>(h->ex_out_r), P, static_cast<const unsigned int*>(ex->flags[ex->rank]),
-        h->ex_seq, h->gstats + GS_XSTATUS);
-    h->stats.total_launches += 2;
+    // (a rank that owns no query still has to run the signal above; its merge is empty.  The wait
+    // for the peers' flags and the status word then happen in a 1-CTA launch over zero queries.)
+    const unsigned int grid = static_cast<unsigned int>(std::max<int64_t>(q_hi - q_lo, 0));
+    if (grid > 0) {
+        merge_topk_kernel<<<grid, SEL_THREADS, smem, h->stream>>>(
+            nq, k, ex->world, reinterpret_cast<const float*>(mine + static_cast<size_t>(nq) * k * 8),
+            reinterpret_cast<const long long*>(mine), ex->slot_bytes / 4, ex->slot_bytes / 8, h->ex_out_s,
+            reinterpret_cast<long long*>(h->ex_out_r), P, static_cast<const unsigned int*>(ex->flags[ex->rank]),
+            h->ex_seq, h->gstats + GS_XSTATUS, q_lo, h->ex_timeout_ns);
+    } else {
+        exchange_wait_kernel<<<1, 32, 0, h->stream>>>(static_cast<const unsigned int*>(ex->flags[ex->rank]),
+                                                      ex->world, h->ex_seq, h->gstats + GS_XSTATUS, h->ex_timeout_ns);
+    }
+    h->stats.total_launches += 1;
     return B2IP_OK;
 }
 
@@ -475,6 +501,11 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
     const CUtensorMap& tmap_x_pair = h->tmap_x_pair;
     const CUtensorMap& tmap_x = h->tmap_x;
 
+    // global threshold round of the peer-direct exchange: one query batch only (the flag carries
+    // one sequence number per search); every rank takes the same decision (same nq, k, budget)
+    const bool thr_round = h->ex && h->ex->gthr[0] && nq <= qb && h->ex->thr_stride >= nq;
+    h->ex_thr = thr_round;
+    const bool fuse_refresh = h->fuse_refresh && !thr_round;
     size_t ev_used = 0;
     std::vector<int> fallback;
     for (int64_t q0 = 0; q0 < nq; q0 += qb) {
@@ -573,20 +604,30 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
                     tmap_q, tmap_x, cp);
             }
             CU_TRY(h, cudaEventRecord(e1, h->stream));
-            // the refresh after the LAST slab is fused into the finalize kernel
-            if (!(last && h->fuse_refresh))
+            // the refresh after the LAST slab is fused into the finalize kernel -- unless this
+            // rank owes its peers a bound for the global threshold (it must exist before finalize)
+            const bool fused = last && fuse_refresh;
+            if (!fused) {
+                PublishBound pub{};
+                if (last && thr_round) {
+                    pub.m_rank = (k + h->ex->world - 1) / h->ex->world;
+                    pub.n_dst = h->ex->world;
+                    for (int r = 0; r < h->ex->world; r++)
+                        pub.dst[r] = static_cast<float*>(h->ex->gthr[r]) + static_cast<size_t>(h->ex->rank) * h->ex->thr_stride + q0;
+                }
                 refresh_threshold_kernel<<<nqb, SEL_THREADS, 0, h->stream>>>(
                     k, cap, cp.cand, cp.cnt, reinterpret_cast<int*>(h->kept.p),
                     reinterpret_cast<float*>(h->thr.p), reinterpret_cast<float*>(h->eps2.p),
-                    reinterpret_cast<int*>(h->flags.p), h->gstats);
+                    reinterpret_cast<int*>(h->flags.p), h->gstats, pub);
+            }
             cudaEvent_t e2 = get_event(h, ev_used++);
             CU_TRY(h, cudaEventRecord(e2, h->stream));
             h->stats.coarse_launches++;
-            h->stats.total_launches += (last && h->fuse_refresh) ? 1 : 2;
+            h->stats.total_launches += fused ? 1 : 2;
             h->stats.slabs++;
             h->stats.coarse_flops += 2.0 * nqb * static_cast<double>(s) * h->d;
             done += s;
-            if (last && h->fuse_refresh) break;
+            if (last) break;
             if (fixed_schedule) {
                 slab = std::max<int64_t>(TILE_X, static_cast<int64_t>(static_cast<double>(done) * (growth - 1.0)));
                 if (n - done - slab < slab / 4) slab = n - done;          // no tiny tail slab
@@ -614,6 +655,10 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             slab = std::max<int64_t>(TILE_X, static_cast<int64_t>(next));
         }
 
+        if (thr_round) {
+            exchange_signal_kernel<<<1, 32, 0, h->stream>>>(peer_flags(h->ex), h->ex_seq, XF_THR, h->gstats, 0);
+            h->stats.total_launches++;
+        }
         FinalizeParams fp{};
         fp.k = k; fp.cap = cap; fp.d = h->d;
         fp.qlist = nullptr;
@@ -630,12 +675,29 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         fp.out_rows = reinterpret_cast<long long*>(d_rows) + q0 * k;
         fp.gstats = h->gstats;
         fp.eps2 = h->two_stage ? reinterpret_cast<const float*>(h->eps2.p) : nullptr;
+        fp.cert_eps2 = reinterpret_cast<const float*>(h->eps2.p);
         fp.n_extra = h->n_extra;
         for (int e = 0; e < h->n_extra; e++) {
             fp.extra_r[e] = reinterpret_cast<long long*>(h->extra_base[e]) + q0 * k;
             fp.extra_s[e] = reinterpret_cast<float*>(h->extra_base[e] + static_cast<size_t>(nq) * k * 8) + q0 * k;
+            fp.extra_rank[e] = h->extra_rank[e];
         }
-        if (h->fuse_refresh) {
+        fp.q_base = q0;
+        if (h->ex && h->ex->gather_mode == B2IP_GATHER_OWNER) {
+            int64_t q_lo, q_hi, per;
+            owner_range(h->ex, nq, &q_lo, &q_hi, &per);
+            fp.owner_per = static_cast<int>(std::max<int64_t>(per, 1));
+            fp.self_rank = h->ex->rank;
+        }
+        if (thr_round) {
+            fp.g_thr = static_cast<const float*>(h->ex->gthr[h->ex->rank]);
+            fp.g_flags = static_cast<const unsigned int*>(h->ex->flags[h->ex->rank]);
+            fp.g_world = h->ex->world;
+            fp.g_stride = h->ex->thr_stride;
+            fp.g_seq = h->ex_seq;
+            fp.g_timeout_ns = h->ex_timeout_ns;
+        }
+        if (fuse_refresh) {
             fp.r_cnt = cp.cnt; fp.r_kept = reinterpret_cast<int*>(h->kept.p);
             fp.r_thr = reinterpret_cast<float*>(h->thr.p);
             fp.r_eps2 = reinterpret_cast<const float*>(h->eps2.p);
@@ -666,6 +728,13 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             CU_TRY(h, cudaStreamSynchronize(h->stream));
         }
         h->stats.rescored += h->h_gstats[GS_RESCORED];
+        {
+            const unsigned int bits = static_cast<unsigned int>(h->h_gstats[GS_MAX_ERR]);
+            float r;
+            memcpy(&r, &bits, sizeof(r));
+            h->stats.max_err_over_eps = std::max(h->stats.max_err_over_eps, static_cast<double>(r));
+            h->stats.bound_violations += h->h_gstats[GS_VIOLATIONS];
+        }
         h->stats.candidates += h->h_gstats[GS_CANDIDATES];
         for (int i = 0; i < static_cast<int>(hflags.size()); i++)
             if (hflags[i] & FLAG_OVERFLOW) fallback.push_back(static_cast<int>(q0 + i));
@@ -724,6 +793,14 @@ int search_device(b2ip_handle h, int64_t nq, const float* dq, int k, float* d_sc
                     reinterpret_cast<long long*>(h->extra_base[e]), nq * k);
             CU_TRY(h, cudaMemsetAsync(h->gstats, 0, GS_COUNT * sizeof(long long), h->stream));
             h->ex_prior_overflow = 0;
+            if (h->ex->gthr[0] && h->ex->thr_stride >= nq) {
+                // no rows, no bound: -inf for every query on every rank, then the threshold flag
+                for (int r = 0; r < h->ex->world; r++)
+                    fill_float_kernel<<<64, 256, 0, h->stream>>>(
+                        static_cast<float*>(h->ex->gthr[r]) + static_cast<size_t>(h->ex->rank) * h->ex->thr_stride,
+                        nq, -INFINITY);
+                exchange_signal_kernel<<<1, 32, 0, h->stream>>>(peer_flags(h->ex), h->ex_seq, XF_THR, h->gstats, 0);
+            }
             RC_TRY(enqueue_exchange(h, nq, k));
             CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
                                       cudaMemcpyDeviceToHost, h->stream));
@@ -836,6 +913,8 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     if (const char* s = getenv("B2IP_HINT_Q")) h->hint_q = atoi(s);
     if (const char* s = getenv("B2IP_HINT_X")) h->hint_x = atoi(s);
     if (const char* s = getenv("B2IP_CAND_BUDGET_MB")) h->cand_budget_bytes = std::max(1ll, atoll(s)) << 20;
+    if (const char* s = getenv("B2IP_EXCHANGE_TIMEOUT_S"))
+        h->ex_timeout_ns = static_cast<long long>(std::max(0.001, atof(s)) * 1e9);
     memset(&h->stats, 0, sizeof(h->stats));
     *out = h;
     return B2IP_OK;
@@ -845,7 +924,7 @@ void b2ip_destroy(b2ip_handle h) {
     if (!h) return;
     Guard g(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-    for (DevBuf* b : {&h->q16, &h->eps2, &h->thr, &h->cnt, &h->kept, &h->flags, &h->cand, &h->qstage,
+    for (DevBuf* b : {&h->q16, &h->eps2, &h->thr, &h->cnt, &h->kept, &h->flags, &h->cand, &h->qstage, &h->qhalf,
                       &h->out_s, &h->out_r, &h->exact_scores, &h->exact_misc, &h->qlist, &h->stage,
                       &h->seg_tab})
         release(*b);
@@ -879,7 +958,12 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     if (n == "gx") h->gx = static_cast<int>(std::max<int64_t>(1, value));
     else if (n == "hint_q") h->hint_q = static_cast<int>(value);
     else if (n == "hint_x") h->hint_x = static_cast<int>(value);
-    else if (n == "dbg") h->dbg = static_cast<int>(value);
+    else if (n == "dbg") {
+        // perf experiments that BREAK results (see CoarseParams::dbg): only with B2IP_DEBUG=1
+        const char* e = getenv("B2IP_DEBUG");
+        if (!e || atoi(e) == 0) return fail(h, B2IP_ERR_INVALID, "option 'dbg' needs B2IP_DEBUG=1 in the environment");
+        h->dbg = static_cast<int>(value);
+    }
     else if (n == "verbose") h->verbose = static_cast<int>(value);
     else if (n == "pair") h->pair = static_cast<int>(value);
     else if (n == "dense_first") h->dense_first = static_cast<int>(value);
@@ -1015,7 +1099,15 @@ int b2ip_set_row_segments(b2ip_handle h, int n_segments, const int64_t* local_st
 
 int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* out_scores,
                 int64_t* out_rows, int mode, int mem) {
+    return b2ip_search_ex(h, nq, queries, B2IP_F32, k, out_scores, out_rows, mode, mem);
+}
+
+int b2ip_search_ex(b2ip_handle h, int64_t nq, const void* queries_any, int q_dtype, int k,
+                   float* out_scores, int64_t* out_rows, int mode, int mem) {
     if (!h) return B2IP_ERR_INVALID;
+    if (q_dtype != B2IP_F32 && q_dtype != B2IP_F16)
+        return fail(h, B2IP_ERR_INVALID, "b2ip_search: q_dtype=%d (use B2IP_F32 or B2IP_F16)", q_dtype);
+    const float* queries = static_cast<const float*>(queries_any);
     if (nq < 0 || (nq > 0 && (!queries || !out_scores || !out_rows)))
         return fail(h, B2IP_ERR_INVALID, "b2ip_search: NULL buffer or nq=%lld", (long long)nq);
     if (k < 1) return fail(h, B2IP_ERR_INVALID, "b2ip_search: k=%d must be >= 1", k);
@@ -1024,12 +1116,32 @@ int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* o
     if (mem != B2IP_MEM_HOST && mem != B2IP_MEM_DEVICE) return fail(h, B2IP_ERR_INVALID, "b2ip_search: mem=%d", mem);
     if (nq >= (1ll << 31)) return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_search: nq too large");
     Guard g(h->device);
-    if (mem == B2IP_MEM_DEVICE) return search_device(h, nq, queries, k, out_scores, out_rows, mode);
     if (nq == 0) { memset(&h->stats, 0, sizeof(h->stats)); h->timing_pending = false; return B2IP_OK; }
-    RC_TRY(ensure(h, h->qstage, static_cast<size_t>(nq) * h->d * sizeof(float)));
+    const size_t q_count = static_cast<size_t>(nq) * h->d;
+    // float16 queries are widened on the GPU: exactly what `query_vectors.astype('float32')`
+    // (src/index.py:35) does on the host, without the host pass and with half the H2D bytes
+    auto widen_queries = [&](const void* half_dev) {
+        const int grid = static_cast<int>(std::min<size_t>((q_count / 2 + 255) / 256 + 1, 65535));
+        widen_f16_kernel<<<grid, 256, 0, h->stream>>>(static_cast<const __half*>(half_dev),
+                                                      static_cast<float*>(h->qstage.p),
+                                                      static_cast<long long>(q_count));
+    };
+    if (mem == B2IP_MEM_DEVICE) {
+        if (q_dtype == B2IP_F32) return search_device(h, nq, queries, k, out_scores, out_rows, mode);
+        RC_TRY(ensure(h, h->qstage, q_count * sizeof(float)));
+        widen_queries(queries_any);
+        return search_device(h, nq, static_cast<const float*>(h->qstage.p), k, out_scores, out_rows, mode);
+    }
+    RC_TRY(ensure(h, h->qstage, q_count * sizeof(float)));
     RC_TRY(ensure(h, h->out_s, static_cast<size_t>(nq) * k * sizeof(float)));
     RC_TRY(ensure(h, h->out_r, static_cast<size_t>(nq) * k * sizeof(int64_t)));
-    RC_TRY(host_to_device(h, h->qstage.p, queries, static_cast<size_t>(nq) * h->d * sizeof(float)));
+    if (q_dtype == B2IP_F16) {
+        RC_TRY(ensure(h, h->qhalf, q_count * 2));
+        RC_TRY(host_to_device(h, h->qhalf.p, queries_any, q_count * 2));
+        widen_queries(h->qhalf.p);
+    } else {
+        RC_TRY(host_to_device(h, h->qstage.p, queries, q_count * sizeof(float)));
+    }
     RC_TRY(search_device(h, nq, static_cast<const float*>(h->qstage.p), k,
                          static_cast<float*>(h->out_s.p), static_cast<int64_t*>(h->out_r.p), mode));
     const size_t sb = static_cast<size_t>(nq) * k * sizeof(float), rb = static_cast<size_t>(nq) * k * sizeof(int64_t);
@@ -1063,10 +1175,14 @@ int b2ip_search_exchange(b2ip_handle h, int64_t nq, const float* queries_dev, in
     // this rank's block goes to slot `rank` of every rank's gather buffer; the local one is the
     // primary output of the finalize kernel, the others its extra (peer) outputs
     char* mine = static_cast<char*>(ex->gather[ex->rank]) + static_cast<size_t>(ex->rank) * ex->slot_bytes;
+    if (ex->gather_mode != B2IP_GATHER_ALL && ex->gather_mode != B2IP_GATHER_OWNER)
+        return fail(h, B2IP_ERR_INVALID, "b2ip_search_exchange: gather_mode=%d", ex->gather_mode);
     h->n_extra = 0;
     for (int p = 0; p < ex->world; p++)
-        if (p != ex->rank)
+        if (p != ex->rank) {
+            h->extra_rank[h->n_extra] = p;
             h->extra_base[h->n_extra++] = static_cast<char*>(ex->gather[p]) + static_cast<size_t>(ex->rank) * ex->slot_bytes;
+        }
     h->ex = ex;
     h->ex_seq = seq;
     h->ex_out_s = out_scores_dev;
@@ -1078,7 +1194,24 @@ int b2ip_search_exchange(b2ip_handle h, int64_t nq, const float* queries_dev, in
     if (rc != B2IP_OK) return rc;
     *status = h->h_gstats[GS_XSTATUS];
     if (*status >= XSTATUS_TIMEOUT)
-        return fail(h, B2IP_ERR_INTERNAL, "b2ip_search_exchange: a peer's results never arrived (seq %u)", seq);
+        return fail(h, B2IP_ERR_INTERNAL,
+                    "b2ip_search_exchange: a peer's flag for search %u did not arrive within %.0f s "
+                    "(B2IP_EXCHANGE_TIMEOUT_S): the peer is gone or stuck; this rank's view of the "
+                    "exchange is no longer consistent with its peers -- tear the process group down",
+                    seq, h->ex_timeout_ns * 1e-9);
+    return B2IP_OK;
+}
+
+int b2ip_enable_peer_access(b2ip_handle h, int peer_device) {
+    if (!h) return B2IP_ERR_INVALID;
+    if (peer_device == h->device) return B2IP_OK;
+    Guard g(h->device);
+    int can = 0;
+    CU_TRY(h, cudaDeviceCanAccessPeer(&can, h->device, peer_device));
+    if (!can) return fail(h, B2IP_ERR_UNSUPPORTED, "device %d cannot access device %d (no P2P path)", h->device, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return B2IP_OK; }
+    CU_TRY(h, e);
     return B2IP_OK;
 }
 
@@ -1105,7 +1238,7 @@ int b2ip_merge_topk_strided(int device, void* cuda_stream, int64_t nq, int k, in
     if (e == cudaSuccess) {
         merge_topk_kernel<<<static_cast<unsigned int>(nq), SEL_THREADS, smem, st>>>(
             nq, k, n_lists, scores, reinterpret_cast<const long long*>(rows), scores_list_stride,
-            rows_list_stride, out_scores, reinterpret_cast<long long*>(out_rows), P, nullptr, 0u, nullptr);
+            rows_list_stride, out_scores, reinterpret_cast<long long*>(out_rows), P, nullptr, 0u, nullptr, 0, 0);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -22,9 +22,51 @@ constexpr int FLAG_OVERFLOW = 1;
 constexpr int EXACT_QB = 8;          // queries per pass of the exact path
 
 // device-side counters of one search (int64 each)
-enum { GS_MAX_KEPT = 0, GS_OVERFLOW = 1, GS_CANDIDATES = 2, GS_RESCORED = 3, GS_XSTATUS = 4, GS_COUNT = 5 };
+enum { GS_MAX_KEPT = 0, GS_OVERFLOW = 1, GS_CANDIDATES = 2, GS_RESCORED = 3, GS_XSTATUS = 4,
+       GS_MAX_ERR = 5,      // run-time certificate: max over rescored rows of |coarse - exact| / eps_q (float bits)
+       GS_VIOLATIONS = 6,   // rescored rows with |coarse - exact| > eps_q (must stay 0)
+       GS_COUNT = 7 };
 constexpr int MAX_PEERS = 8;         // ranks of one NVSwitch box in the peer-direct exchange
 constexpr long long XSTATUS_TIMEOUT = 1ll << 40;   // GS_XSTATUS: a peer's flag never arrived
+// Flag array of one parity: XF_WORDS uint32 per rank.  Rank r publishes into words
+// [XF_WORDS*r ...) of EVERY rank's array.
+constexpr int XF_WORDS = 4;
+enum { XF_RESULT = 0,     // = seq once rank r's result blocks of search `seq` are in my gather buffer
+       XF_OVERFLOW = 1,   // rank r's overflowed queries in that search
+       XF_THR = 2 };      // = seq once rank r's per-query bounds are in my threshold buffer
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Threads 0..world-1 of the block wait until word `word` of every rank's flag group has reached
+// `seq` (acquire, system scope), bounded by `timeout_ns` of wall time: a dead peer must not hang
+// the GPU -- it leaves XSTATUS_TIMEOUT in *xstatus and the call fails on the host.  Ends with a
+// block barrier.
+__device__ __forceinline__ void wait_peer_flags(const unsigned int* flags, int world, int word,
+                                                unsigned int seq, long long timeout_ns,
+                                                long long* xstatus) {
+    if (threadIdx.x < world) {
+        const unsigned int* f = flags + XF_WORDS * threadIdx.x + word;
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (static_cast<int>(v - seq) < 0) {
+            const unsigned long long t0 = global_timer_ns();
+            for (;;) {
+                __nanosleep(200);
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (static_cast<int>(v - seq) >= 0) break;
+                if (static_cast<long long>(global_timer_ns() - t0) > timeout_ns) {
+                    if (xstatus) atomicMax(xstatus, XSTATUS_TIMEOUT);
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -446,20 +488,49 @@ __device__ int refresh_list(int q, int k, int cap, unsigned long long* __restric
     return m;
 }
 
+// Global threshold of the row-sharded search (peer-direct exchange): after its last slab every
+// rank publishes, per query, its m-th largest coarse score with m = ceil(k / world) -- into the
+// threshold buffer of EVERY rank (NVLink P2P stores).  On each rank at least m rows score >= its
+// own bound, so world * m >= k rows of the whole corpus score >= T = min over ranks: T is a lower
+// bound on the global k-th coarse score, and rows with coarse < T - 2 eps cannot be in the global
+// exact top-k.  A rank holding fewer than m candidates publishes -inf (no bound).
+struct PublishBound {
+    int m_rank;                       // 0 = nothing to publish
+    int n_dst;
+    float* dst[MAX_PEERS];            // dst[i][q]: this rank's row of rank i's threshold buffer
+};
+
 __global__ void __launch_bounds__(SEL_THREADS)
 refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
                          int* __restrict__ cnt, int* __restrict__ kept, float* __restrict__ thr,
                          const float* __restrict__ eps2, int* __restrict__ flags,
-                         long long* __restrict__ gstats) {
+                         long long* __restrict__ gstats, const PublishBound pub) {
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_krem;
     __shared__ int s_warp[SEL_THREADS / 32];
     __shared__ unsigned long long skeys[REFRESH_SMEM_KEYS];
     const int q = blockIdx.x;
-    if (flags[q] & FLAG_OVERFLOW) return;
-    refresh_list(q, k, cap, cand, cnt, kept, thr, eps2, flags, gstats, skeys, hist, &s_prefix,
-                 &s_krem, s_warp);
+    int n = -1;
+    if (!(flags[q] & FLAG_OVERFLOW))
+        n = refresh_list(q, k, cap, cand, cnt, kept, thr, eps2, flags, gstats, skeys, hist, &s_prefix,
+                         &s_krem, s_warp);
+    if (pub.m_rank > 0) {
+        float bound = -INFINITY;
+        if (n >= pub.m_rank) {
+            __syncthreads();                         // the compacted list is visible to every warp
+            const unsigned long long pk = block_radix_select(cand + static_cast<long long>(q) * cap, n,
+                                                             pub.m_rank, 4, hist, &s_prefix, &s_krem);
+            if ((pk >> 32) != 0ull) bound = unorder_f32(static_cast<uint32_t>(pk >> 32));   // 0 = a NaN score
+        }
+        if (threadIdx.x < pub.n_dst) pub.dst[threadIdx.x][q] = bound;
+    }
+}
+
+__global__ void fill_float_kernel(float* dst, long long count, float v) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dst[i] = v;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -475,6 +546,7 @@ struct FinalizeParams {
     // kept counts, thresholds, bounds and flags the refresh kernel would have updated
     int* r_cnt; int* r_kept; float* r_thr; const float* r_eps2; int* r_flags;
     const float* eps2;                // [slots] 2*eps per query: enables the two-stage rescore
+    const float* cert_eps2;           // [slots] 2*eps per query: run-time check |coarse - exact| <= eps (or nullptr)
     const float* q32;                 // [*, d] fp32 queries (rescore)
     const float* x32;                 // [n, d] fp32 corpus (rescore), or nullptr:
     const __nv_bfloat16* x16;         // [n, d_pad] 16-bit corpus when the index stores bf16 / fp16
@@ -491,6 +563,19 @@ struct FinalizeParams {
     int n_extra;
     float* extra_s[MAX_PEERS - 1];
     long long* extra_r[MAX_PEERS - 1];
+    // owner mode (owner_per > 0): query q of the search belongs to rank q / owner_per and its block
+    // is stored ONLY there (locally when that is self_rank, else into extra slot e with
+    // extra_rank[e] == owner): 1/world of the peer traffic, and the merge of a query runs once
+    int owner_per, self_rank;
+    int extra_rank[MAX_PEERS - 1];
+    long long q_base;                 // index of slot 0 in the whole search (query batches)
+    // global threshold round (g_thr != nullptr): wait for every rank's bound, prune with the minimum
+    const float* g_thr;               // [g_world, g_stride] this rank's threshold buffer
+    const unsigned int* g_flags;      // this rank's flag array of the parity
+    int g_world;
+    long long g_stride;
+    unsigned int g_seq;
+    long long g_timeout_ns;
     long long* gstats;
 };
 
@@ -521,6 +606,8 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
     __shared__ int s_krem;
     __shared__ int s_warp[SEL_THREADS / 32];
     __shared__ unsigned int s_min;
+    __shared__ unsigned int s_err;      // max |coarse - exact| / eps of this query (float bits, >= 0)
+    __shared__ unsigned int s_viol;
 
     const int slot = blockIdx.x;
     if (p.flags && (p.flags[slot] & FLAG_OVERFLOW)) return;
@@ -539,11 +626,44 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
     unsigned long long* keys = p.cand + static_cast<long long>(slot) * p.cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
+    if (kRescore && p.g_thr) {
+        // row-sharded search: every rank's bound for this query is (about to be) in my threshold
+        // buffer; T = their minimum bounds the GLOBAL k-th coarse score from below (PublishBound)
+        wait_peer_flags(p.g_flags, p.g_world, XF_THR, p.g_seq, p.g_timeout_ns,
+                        p.gstats ? p.gstats + GS_XSTATUS : nullptr);
+        float T = INFINITY;
+        for (int r = 0; r < p.g_world; r++) {
+            const float b = p.g_thr[r * p.g_stride + p.q_base + slot];
+            T = (b == b) ? fminf(T, b) : -INFINITY;
+        }
+        float tg = __fsub_rd(T, p.cert_eps2[slot]);
+        if (!(tg == tg)) tg = -INFINITY;
+        tg = nextafterf(tg, -INFINITY);              // kept: coarse > tg
+        if (tg > -INFINITY && n > 0) {
+            n = block_compact(keys, n, false, order_f32(tg), 0ull, keys, s_warp);
+            __syncthreads();
+        }
+    }
+
     if (kRescore) {
+        if (threadIdx.x == 0) { s_err = 0u; s_viol = 0u; }
         for (int j = threadIdx.x; j < p.d; j += blockDim.x)
             sq[j] = static_cast<double>(p.q32[static_cast<long long>(q) * p.d + j]);
         __syncthreads();
         const double2* q2 = reinterpret_cast<const double2*>(sq);
+        // Run-time certificate of the a-priori bound eps_q (prep_queries_kernel): every row that is
+        // rescored anyway still carries its COARSE score in the key, so |coarse - exact| / eps_q is
+        // free to check.  It is the only guard on the tensor core's fp32 accumulation behaviour.
+        const float cert_eps = p.cert_eps2 ? 0.5f * p.cert_eps2[slot] : 0.f;
+        const bool cert = p.gstats && cert_eps > 0.f && cert_eps <= FLT_MAX;
+        auto certify = [&](unsigned long long coarse_key, float exact) {
+            const float c = key_score(coarse_key);
+            const float e = fabsf(c - exact);
+            if (!(e <= FLT_MAX)) return;            // NaN / inf scores carry no margin (see shadow_rows_kernel)
+            const float ratio = e / cert_eps;
+            atomicMax(&s_err, __float_as_uint(ratio));
+            if (ratio > 1.0f) atomicAdd(&s_viol, 1u);
+        };
         // keys[lo..hi) <- exact (score,row) keys.  Two candidates per warp iteration: both rows'
         // loads are in flight before either reduction starts (the gather is latency-bound: 3 KB
         // from a random HBM page per row).  track_min: s_min <- smallest exact score (ordered).
@@ -571,6 +691,10 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
                 acc2 = warp_sum(acc2);
                 if (lane == 0) {
                     const float s1 = static_cast<float>(acc), s2 = static_cast<float>(acc2);
+                    if (cert) {
+                        certify(keys[i], s1);
+                        if (has2) certify(keys[i2], s2);
+                    }
                     keys[i] = make_key(s1, row);   // NaN -> high word 0
                     if (has2) keys[i2] = make_key(s2, row2);
                     if (track_min) {
@@ -608,10 +732,15 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
         } else {
             rescore_range(0, n, false);
         }
-        if (threadIdx.x == 0 && p.gstats)
+        __syncthreads();
+        if (threadIdx.x == 0 && p.gstats) {
             atomicAdd(reinterpret_cast<unsigned long long*>(p.gstats + GS_RESCORED),
                       static_cast<unsigned long long>(n_resc));
-        __syncthreads();
+            if (s_err) atomicMax(reinterpret_cast<unsigned long long*>(p.gstats + GS_MAX_ERR),
+                                 static_cast<unsigned long long>(s_err));
+            if (s_viol) atomicAdd(reinterpret_cast<unsigned long long*>(p.gstats + GS_VIOLATIONS),
+                                  static_cast<unsigned long long>(s_viol));
+        }
         n = n_resc;
     }
 
@@ -651,11 +780,16 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
             }
         }
         const long long o = static_cast<long long>(q) * p.k + j;
-        p.out_scores[o] = s;
-        p.out_rows[o] = r;
+        const int owner = p.owner_per > 0 ? static_cast<int>((p.q_base + q) / p.owner_per) : -1;
+        if (owner < 0 || owner == p.self_rank) {
+            p.out_scores[o] = s;
+            p.out_rows[o] = r;
+        }
         for (int e = 0; e < p.n_extra; e++) {
-            p.extra_s[e][o] = s;
-            p.extra_r[e][o] = r;
+            if (owner < 0 || owner == p.extra_rank[e]) {
+                p.extra_s[e][o] = s;
+                p.extra_r[e][o] = r;
+            }
         }
     }
 }
@@ -798,19 +932,35 @@ exact_collect_kernel(const float* __restrict__ scores, long long n, const ExactS
 // ---------------------------------------------------------------------------------------
 struct PeerFlags {
     int world, rank;
-    unsigned int* flags[MAX_PEERS];   // flags[p] = rank p's flag array of this parity, [2 * world]
+    unsigned int* flags[MAX_PEERS];   // flags[p] = rank p's flag array of this parity, [XF_WORDS * world]
 };
-// Launched after the finalize kernel on the same stream: the kernel boundary makes finalize's
-// stores (local and peer) performed, the system fence orders them before the flag.
-__global__ void exchange_signal_kernel(PeerFlags pf, unsigned int seq, const long long* __restrict__ gstats,
-                                       long long prior_overflow) {
+// Launched after the kernel whose peer stores it announces, on the same stream: the kernel
+// boundary makes those stores (local and peer) performed, the system fence orders them before
+// the flag.  word = XF_RESULT (after finalize; also publishes the overflow count) or XF_THR
+// (after the last refresh).
+__global__ void exchange_signal_kernel(PeerFlags pf, unsigned int seq, int word,
+                                       const long long* __restrict__ gstats, long long prior_overflow) {
     const int p = threadIdx.x;
     if (p >= pf.world) return;
-    unsigned int* f = pf.flags[p] + 2 * pf.rank;
-    const long long ov = gstats[GS_OVERFLOW] + prior_overflow;
-    f[1] = ov > 0x7fffffffll ? 0x7fffffffu : static_cast<unsigned int>(ov);
+    unsigned int* f = pf.flags[p] + XF_WORDS * pf.rank;
+    if (word == XF_RESULT) {
+        const long long ov = gstats[GS_OVERFLOW] + prior_overflow;
+        f[XF_OVERFLOW] = ov > 0x7fffffffll ? 0x7fffffffu : static_cast<unsigned int>(ov);
+    }
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f + word), "r"(seq) : "memory");
+}
+
+// A rank that owns no query of a search (owner mode, nq < world) has nothing to merge but still
+// reports the exchange status (overflows, timeouts) like everyone else.
+__global__ void exchange_wait_kernel(const unsigned int* wait_flags, int world, unsigned int seq,
+                                     long long* __restrict__ xstatus, long long timeout_ns) {
+    wait_peer_flags(wait_flags, world, XF_RESULT, seq, timeout_ns, xstatus);
+    if (threadIdx.x == 0) {
+        long long ov = 0;
+        for (int l = 0; l < world; l++) ov += wait_flags[XF_WORDS * l + XF_OVERFLOW];
+        atomicMax(xstatus, ov);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -831,34 +981,23 @@ merge_topk_kernel(long long nq, int k, int n_lists, const float* __restrict__ sc
                   const long long* __restrict__ rows, long long scores_list_stride,
                   long long rows_list_stride, float* __restrict__ out_scores,
                   long long* __restrict__ out_rows, int P, const unsigned int* wait_flags,
-                  unsigned int seq, long long* __restrict__ xstatus) {
+                  unsigned int seq, long long* __restrict__ xstatus, long long q_first,
+                  long long timeout_ns) {
     extern __shared__ __align__(16) uint8_t msm[];
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(msm);
-    const long long q = blockIdx.x;
+    // owner mode: this rank merges queries [q_first, q_first + gridDim.x) of the search and
+    // stores them compactly (row 0 of the output = query q_first)
+    const long long q = q_first + blockIdx.x;
+    const long long qo = blockIdx.x;
     const int total = n_lists * k;
     if (wait_flags) {
         // peer-direct exchange: list l was stored into this GPU's memory by rank l's finalize
-        // kernel; rank l then published flag word 2l = seq (release, system scope) and its
-        // overflow count in word 2l+1.  Wait for all of them (bounded: a dead peer must not
-        // hang the GPU), then merge as usual.
-        if (threadIdx.x < n_lists) {
-            const unsigned int* f = wait_flags + 2 * threadIdx.x;
-            const long long t0 = clock64();
-            unsigned int v;
-            for (;;) {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                if (static_cast<int>(v - seq) >= 0) break;
-                if (clock64() - t0 > 8000000000ll) {                  // ~4-6 s
-                    if (xstatus) atomicMax(xstatus, XSTATUS_TIMEOUT);
-                    break;
-                }
-                __nanosleep(100);
-            }
-        }
-        __syncthreads();
+        // kernel; rank l then published XF_RESULT = seq (release, system scope) and its overflow
+        // count.  Wait for all of them, then merge as usual.
+        wait_peer_flags(wait_flags, n_lists, XF_RESULT, seq, timeout_ns, xstatus);
         if (xstatus && blockIdx.x == 0 && threadIdx.x == 0) {
             long long ov = 0;
-            for (int l = 0; l < n_lists; l++) ov += wait_flags[2 * l + 1];
+            for (int l = 0; l < n_lists; l++) ov += wait_flags[XF_WORDS * l + XF_OVERFLOW];
             atomicMax(xstatus, ov);
         }
     }
@@ -879,8 +1018,8 @@ merge_topk_kernel(long long nq, int k, int n_lists, const float* __restrict__ sc
         float s = -FLT_MAX;
         long long r = -1;
         if ((key >> 32) != 0ull) { s = key_score(key); r = key_row(key); }
-        out_scores[q * k + j] = s;
-        out_rows[q * k + j] = r;
+        out_scores[qo * k + j] = s;
+        out_rows[qo * k + j] = r;
     }
 }
 

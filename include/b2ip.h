@@ -54,7 +54,7 @@ enum { B2IP_MEM_HOST = 0, B2IP_MEM_DEVICE = 1 };
 
 /* search strategy */
 enum {
-    B2IP_MODE_AUTO = 0,   /* tensor path; tiny problems take the exact path            */
+    B2IP_MODE_AUTO = 0,   /* = B2IP_MODE_TENSOR (queries whose candidate list overflows are re-run exactly) */
     B2IP_MODE_TENSOR = 1, /* tcgen05 bf16 coarse GEMM + fused threshold filter, fp32 rescore */
     B2IP_MODE_EXACT = 2   /* fp32 FMA scores + radix select (also the overflow fallback) */
 };
@@ -79,6 +79,10 @@ typedef struct b2ip_stats_s {
     int32_t query_batches;
     float refresh_ms;            /* sum of the threshold-refresh kernel durations          */
     float finalize_ms;           /* rescore + final select/sort kernel durations           */
+    /* run-time certificate of the coarse pass's a-priori error bound eps_q: over every row the
+     * search rescored, max |coarse - exact| / eps_q (must stay < 1) and the number of rows above 1 */
+    double max_err_over_eps;
+    int64_t bound_violations;
 } b2ip_stats_t;
 
 /* replaces faiss.IndexFlatIP(vector_sz)                       -- src/index.py:21
@@ -133,6 +137,13 @@ int b2ip_set_row_segments(b2ip_handle h, int n_segments, const int64_t* local_st
 int b2ip_search(b2ip_handle h, int64_t nq, const float* queries, int k, float* out_scores,
                 int64_t* out_rows, int mode, int mem);
 
+/* Same with the queries' element type stated: B2IP_F32 or B2IP_F16.  The reference's default
+ * pipeline hands float16 query embeddings (passage_retrieval.py:154-155) to
+ * `query_vectors.astype('float32')` (src/index.py:35); float16 queries are widened on the GPU
+ * instead (exact, so results are identical) -- no host pass, half the host->device bytes. */
+int b2ip_search_ex(b2ip_handle h, int64_t nq, const void* queries, int q_dtype, int k,
+                   float* out_scores, int64_t* out_rows, int mode, int mem);
+
 /* The one exchange step of the row-sharded search: merges n_lists per-shard results
  * (scores [n_lists,nq,k] descending per list, rows [n_lists,nq,k] global ids, -1 padded)
  * into the global top-k (score desc, ties -> lower row).  All pointers are DEVICE
@@ -150,27 +161,53 @@ int b2ip_merge_topk_strided(int device, void* cuda_stream, int64_t nq, int k, in
 
 /* The same exchange fused behind the search, over peer memory instead of a collective call.
  * Every rank owns a `gather` buffer of `world` slots ([rows int64 nq*k | scores fp32 nq*k],
- * slot_bytes apart) and a flag array uint32[2*world], both mapped into every other rank's address
- * space (CUDA IPC / torch symmetric memory; NVLink P2P).  b2ip_search_exchange runs the local
+ * slot_bytes apart) and a flag array uint32[4*world], both mapped into every other rank's address
+ * space (CUDA IPC / torch symmetric memory, or plain peer access inside one process; NVLink
+ * P2P).  b2ip_search_exchange runs the local
  * search with its finalize kernel storing this rank's [nq,k] block straight into slot `rank` of
- * EVERY rank's gather buffer, publishes flags[p][2*rank] = seq on every rank p, and merges the
+ * EVERY rank's gather buffer, publishes flags[p][4*rank] = seq on every rank p, and merges the
  * world's blocks out of its own gather buffer as soon as all flags are in -- two launches queued
  * behind the search on the same stream, no host round trip and no separate all-gather.
  * Callers alternate between two buffer sets (seq parity): a rank can run at most one search
  * ahead of its slowest peer.  *status = total number of queries, over all ranks, whose candidate
  * lists overflowed (identical on every rank): when non-zero the merged output is not valid and
  * every rank must repeat the search through b2ip_search + all-gather + b2ip_merge_topk.
+ *
+ * Two refinements remove the per-rank work that would otherwise not shrink with the number of GPUs:
+ *   - global threshold (gthr != NULL): after its last corpus slab every rank stores, per query, its
+ *     ceil(k/world)-th largest coarse score into EVERY rank's threshold buffer gthr[p] (float
+ *     [world][thr_stride], row = publishing rank) and raises a second flag; the minimum over ranks is
+ *     a lower bound on the GLOBAL k-th coarse score, so each rank rescores only its candidates above
+ *     that bound minus the error margin (about k/world + a few rows instead of k + a window).
+ *   - B2IP_GATHER_OWNER: query q belongs to rank q / ceil(nq/world); a rank's block for q is stored
+ *     only into the owner's gather buffer, the owner alone merges it, and out_scores/out_rows hold
+ *     just the owned queries [q_lo, q_hi) compactly ([q_hi-q_lo, k]).  B2IP_GATHER_ALL: every rank
+ *     receives and merges everything (out buffers [nq,k]).
+ * flags[p] is uint32[4*world]: per publishing rank {results seq, overflow count, thresholds seq, 0}.
+ * A flag that does not arrive within B2IP_EXCHANGE_TIMEOUT_S (environment, default 600 s) makes the
+ * call fail with B2IP_ERR_INTERNAL: treat it like a collective timeout (the process group is dead).
  * All pointers are device pointers valid on the handle's device; queries [nq,d] fp32. */
 #define B2IP_MAX_PEERS 8
+enum { B2IP_GATHER_ALL = 0, B2IP_GATHER_OWNER = 1 };
 typedef struct b2ip_exchange_s {
     int32_t world, rank;
     int64_t slot_bytes;
     void* gather[B2IP_MAX_PEERS];   /* gather[p]: rank p's gather buffer of this parity */
-    void* flags[B2IP_MAX_PEERS];    /* flags[p]:  rank p's uint32[2*world] flag array of this parity */
+    void* flags[B2IP_MAX_PEERS];    /* flags[p]:  rank p's uint32[4*world] flag array of this parity */
+    void* gthr[B2IP_MAX_PEERS];     /* gthr[p]:   rank p's float[world*thr_stride] threshold buffer, or all NULL */
+    int64_t thr_stride;             /* floats per publishing rank in gthr (>= nq) */
+    int32_t gather_mode;            /* B2IP_GATHER_ALL / B2IP_GATHER_OWNER */
+    int32_t reserved;
 } b2ip_exchange_t;
 int b2ip_search_exchange(b2ip_handle h, int64_t nq, const float* queries_dev, int k,
                          const b2ip_exchange_t* ex, uint32_t seq, float* out_scores_dev,
                          int64_t* out_rows_dev, int64_t* status);
+
+/* One process driving several GPUs (the reference driver is a single process): lets kernels of
+ * this handle's device store into buffers that live on `peer_device` (cudaDeviceEnablePeerAccess),
+ * so b2ip_search_exchange can be used between handles of the same process with plain device
+ * pointers in b2ip_exchange_t.  Fails with B2IP_ERR_UNSUPPORTED when the devices have no P2P path. */
+int b2ip_enable_peer_access(b2ip_handle h, int peer_device);
 
 /* replaces faiss.write_index's read of the stored vectors       -- src/index.py:53
  * Copies rows [row0, row0+n) as fp32 into out ([n,d]). */

@@ -6,7 +6,8 @@ cpu_baseline / `--impl reference` legs of bench.py, never by the product package
 
 PARITY UNPINNED (see flatip_oracle.c): faiss-cpu==1.8.0 (reference environment.yml:138) is
 not installable offline and the reference holds no golden vectors for this path.  The
-restatement is pinned against `brute_force_f64` below instead.
+restatement is pinned against `brute_force_f64` below instead.  `real_faiss()` is the hook
+that replaces it with the real library wherever `import faiss` succeeds.
 
 `OracleIndexer` restates the reference's `Indexer` (src/index.py:15-73) over the oracle
 search so that parity tests can be written as "same calls on both objects".
@@ -93,10 +94,39 @@ def num_threads() -> int:
     return int(_load().oracle_num_threads())
 
 
-def search(queries: np.ndarray, corpus: np.ndarray, k: int, use_blas: bool = True
-           ) -> Tuple[np.ndarray, np.ndarray]:
-    """faiss-1.8.0-equivalent `IndexFlatIP.search`: returns (D float32 [nq,k] descending,
-    I int64 [nq,k]); (-FLT_MAX, -1) padding when the corpus has fewer than k rows."""
+def real_faiss():
+    """The reference's own library when it is importable (faiss-cpu==1.8.0, reference
+    environment.yml:138), else None.  It is NOT installable offline in this image (SURVEY.md
+    8c); the day `import faiss` works, `search` / `make_index` below -- and with them every
+    parity test, smoke() and both CPU legs of bench.py -- switch to it, and tests/test_oracle.py
+    additionally checks the restatement and the index.faiss writer against it.
+    B2IP_ORACLE_FAISS=0 keeps the restatement."""
+    if os.environ.get("B2IP_ORACLE_FAISS", "1") == "0":
+        return None
+    try:
+        import faiss
+        return faiss
+    except ImportError:
+        return None
+
+
+def backend_kind() -> str:
+    """bench.py's `cpu_baseline.kind`: "reference" = real faiss, "port" = the restatement."""
+    return "reference" if real_faiss() is not None else "port"
+
+
+def backend_description() -> str:
+    f = real_faiss()
+    if f is not None:
+        return f"faiss {getattr(f, '__version__', '?')} IndexFlatIP.search, {f.omp_get_max_threads()} OpenMP threads"
+    return ("faiss-IndexFlatIP-equivalent CPU restatement (faiss-cpu 1.8.0 not installable offline), BLAS: "
+            + blas_description())
+
+
+def restatement_search(queries: np.ndarray, corpus: np.ndarray, k: int, use_blas: bool = True
+                       ) -> Tuple[np.ndarray, np.ndarray]:
+    """oracle/flatip_oracle.c: returns (D float32 [nq,k] descending, I int64 [nq,k]);
+    (-FLT_MAX, -1) padding when the corpus has fewer than k rows."""
     q = np.ascontiguousarray(queries, dtype=np.float32)
     x = np.ascontiguousarray(corpus, dtype=np.float32)
     assert q.ndim == 2 and x.ndim == 2 and q.shape[1] == x.shape[1], (q.shape, x.shape)
@@ -111,6 +141,38 @@ def search(queries: np.ndarray, corpus: np.ndarray, k: int, use_blas: bool = Tru
     if rc != 0:
         raise RuntimeError(f"oracle_flatip_search failed rc={rc}")
     return D, I
+
+
+class FlatIndex:
+    """`faiss.IndexFlatIP(d)` + `add(corpus)` once, `search` many times (reference
+    src/index.py:21,30,42): real faiss when importable, else the restatement over the caller's
+    array (no copy)."""
+
+    def __init__(self, corpus: np.ndarray):
+        self.corpus = corpus
+        self._faiss_index = None
+        f = real_faiss()
+        if f is not None:
+            self._faiss_index = f.IndexFlatIP(int(corpus.shape[1]))
+            self._faiss_index.add(np.ascontiguousarray(corpus, dtype=np.float32))
+
+    def search(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        if self._faiss_index is not None:
+            return self._faiss_index.search(np.ascontiguousarray(queries, dtype=np.float32), int(k))
+        return restatement_search(queries, self.corpus, k)
+
+
+def make_index(corpus: np.ndarray) -> FlatIndex:
+    return FlatIndex(corpus)
+
+
+def search(queries: np.ndarray, corpus: np.ndarray, k: int, use_blas: bool = True
+           ) -> Tuple[np.ndarray, np.ndarray]:
+    """The oracle: `faiss.IndexFlatIP(d).add(corpus).search(queries, k)` -- real faiss when it
+    is importable, else the restatement."""
+    if use_blas and real_faiss() is not None:
+        return FlatIndex(corpus).search(queries, k)
+    return restatement_search(queries, corpus, k, use_blas)
 
 
 def brute_force_f64(queries: np.ndarray, corpus: np.ndarray, k: int,

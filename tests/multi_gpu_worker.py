@@ -38,6 +38,47 @@ for k in (10, 100, 1000):
         D2, I2 = idx2.search(qd, k)
         assert torch.equal(I2, Iw) and torch.equal(D2, Dw), f"k={k} peer={peer}: replicated ingest differs"
 
+# owner mode + global threshold round: every rank holds the global answer of the queries it owns;
+# with the threshold round each rank rescores about k/world rows instead of k + a window
+for k in (10, 100, 1000):
+    Dw, Iw = whole.search(qd, k)
+    for gthr in (True, False):
+        idx = ShardedIndex(d, device=local)
+        idx.global_threshold = gthr
+        lo, hi = shard_bounds(n, world, rank)
+        idx.add_local(x[lo:hi], lo)
+        D, I, (qlo, qhi) = idx.search_owned(qd, k)
+        assert (qlo, qhi) == shard_bounds(nq, world, rank) and D.shape == (qhi - qlo, k)
+        assert torch.equal(I, Iw[qlo:qhi]) and torch.equal(D, Dw[qlo:qhi]), f"k={k} gthr={gthr}: owned slice differs"
+        st = idx.engine.stats()
+        assert st["bound_violations"] == 0 and st["max_err_over_eps"] < 1.0
+        resc = st["rescored"] / nq
+        if gthr:
+            assert idx.exchange_searches == 1
+            resc_with = resc
+        else:
+            assert resc_with <= resc, (k, resc_with, resc)
+        D2, I2 = idx.search(qd, k)                       # the all-ranks form over the same buffers
+        assert torch.equal(I2, Iw) and torch.equal(D2, Dw)
+    # host buffers in, this rank's slice out (the e2e call of bench.py at N > 1)
+    Dh = np.full((nq, k), np.nan, np.float32); Ih = np.full((nq, k), -7, np.int64)
+    for qq in (q, q.astype(np.float16)):
+        Dref, Iref = whole.search(torch.from_numpy(qq.astype(np.float32)).cuda(), k)
+        _, _, (qlo, qhi) = idx.search_host(qq, k, out=(Dh, Ih))
+        assert np.array_equal(Ih[qlo:qhi], Iref[qlo:qhi].cpu().numpy()) and np.array_equal(Dh[qlo:qhi], Dref[qlo:qhi].cpu().numpy())
+# fewer queries than ranks (a rank that owns nothing), and an empty shard, in owner mode
+idx_o = ShardedIndex(d, device=local)
+idx_e = ShardedIndex(d, device=local)
+lo, hi = shard_bounds(n, world, rank)
+idx_o.add_local(x[lo:hi], lo)
+if rank == 0:
+    idx_e.add_local(x, 0)
+for nqs in (1, max(1, world - 1), world, 3 * world + 1, 500):
+    Dw, Iw = whole.search(qd[:nqs].contiguous(), 10)
+    for index in (idx_o, idx_e):
+        D, I, (qlo, qhi) = index.search_owned(qd[:nqs].contiguous(), 10)
+        assert torch.equal(I, Iw[qlo:qhi]) and torch.equal(D, Dw[qlo:qhi]), f"owned search nq={nqs} differs"
+
 # peer-direct exchange over many searches: both parities, buffers regrown, batch sizes of the
 # latency regime, and a rank with an EMPTY shard
 idx = ShardedIndex(d, device=local)
@@ -69,11 +110,22 @@ if rank == 0:
     from b2ip import MultiGpuEngine
     m = MultiGpuEngine(d)
     assert len(m.engines) >= world
-    m.add(x[:25_000]); m.add(x[25_000:])
+    m.add(x[:25_000]); m.add(x[25_000:25_003]); m.add(x[25_003:])
+    assert max(mp.n_local for mp in m.maps) - min(mp.n_local for mp in m.maps) <= 1
     for k in (10, 100):
         Dw, Iw = whole.search(q, k)
         Dm, Im = m.search(q, k)
         assert np.array_equal(Im, Iw) and np.array_equal(Dm, Dw), f"k={k}: MultiGpuEngine differs"
+        Dm, Im = m.search(q.astype(np.float16), k)        # float16 queries are widened on the device
+        Dh, Ih = whole.search(q.astype(np.float16), k)
+        assert np.array_equal(Im, Ih) and np.array_equal(Dm, Dh)
+        Dt, It = m.search(qd, k)                           # device queries in, tensors out
+        assert torch.equal(It.cpu(), torch.from_numpy(Iw)) and torch.equal(Dt.cpu(), torch.from_numpy(Dw))
+    assert m.exchange_searches == 6, m.exchange_searches   # the fused exchange, not the copy-and-merge path
+    for nqs in (1, 3):
+        Dw, Iw = whole.search(q[:nqs], 10)
+        Dm, Im = m.search(q[:nqs], 10)
+        assert np.array_equal(Im, Iw) and np.array_equal(Dm, Dw)
     m.close()
 dist.barrier()
 dist.destroy_process_group()

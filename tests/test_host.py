@@ -179,6 +179,11 @@ D, I = idx.search(torch.from_numpy(q), k)
 D64, I64 = fo.brute_force_f64(q, x, k)
 fo.compare_topk(D.numpy(), I.numpy(), D64.astype(np.float32), I64, q, x, rtol=1e-5)
 assert np.array_equal(I.numpy(), I64), "ties must resolve to the lower GLOBAL row"
+# the partitioned form: every rank holds the answer of the queries it owns
+Do, Io, (qlo, qhi) = idx.search_owned(torch.from_numpy(q), k)
+from b2ip.sharded import shard_bounds as sb
+assert (qlo, qhi) == sb(len(q), world, rank) and np.array_equal(Io.numpy(), I64[qlo:qhi])
+assert np.array_equal(Do.numpy(), D.numpy()[qlo:qhi])
 # contiguous sharding through add_local + shard_bounds gives the same answer
 from b2ip.sharded import shard_bounds
 idx2 = ShardedIndex(d, engine=OracleEngine(d), merge_fn=merge)
@@ -212,15 +217,30 @@ def test_sharded_search_gloo_world2(tmp_path):
 
 
 def test_bench_reference_arm_prints_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1", "--cpu-sample-rows", "20000", "--cpu-sample-queries", "64"],
-                         capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
+    """`--impl reference` under a torchrun-like environment (OMP_NUM_THREADS=1 exported): the CPU
+    arm must take every host core anyway, search the FULL (here: small) corpus, and report the
+    duration of what it actually ran as ms_per_step."""
     import json
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--n-corpus", "30000", "--ref-queries", "64",
+                          "--extra-cpu-legs", "c5:1,c5:64"],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] == len(os.sched_getaffinity(0))
+    assert cb["rows"] == 30000 and cb["queries_per_step"] == 64 and cb["scaled_to"] is None
+    # value and ms_per_step describe the same measured step: nothing is extrapolated
+    assert abs(line["value"] - 64 / (line["ms_per_step"] / 1e3)) <= 1e-6 * line["value"]
+    assert [e["batch"] for e in cb["extra_legs"]] == [1, 64]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("C3")
+    # the other ranks of a torchrun launch print nothing and exit 0
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
 
 
 class _RecordingIndex:
@@ -339,6 +359,25 @@ def test_segment_map_local_to_global(built):
         m.append(900, 1)
 
 
+def test_multi_engine_levels_its_shards(built):
+    """MultiGpuEngine.add cuts every chunk so the shards' totals stay level (the
+    remainder used to go to the lowest-numbered devices), whatever the chunk sizes."""
+    import random
+    from b2ip.multi import level_split
+    rnd = random.Random(3)
+    for _ in range(3000):
+        G = rnd.randint(1, 8)
+        tot = [0] * G
+        for _ in range(rnd.randint(1, 12)):
+            n = rnd.choice([0, 1, 2, G - 1, G, G + 1, rnd.randint(0, 50)])
+            take = level_split(tot, n)
+            assert sum(take) == n and min(take) >= 0
+            tot = [a + b for a, b in zip(tot, take)]
+            assert max(tot) - min(tot) <= 1, tot
+    assert level_split([0, 0, 0, 0], 3) in ([1, 1, 1, 0], [0, 1, 1, 1], [1, 0, 1, 1], [1, 1, 0, 1])
+    assert level_split([3, 2, 2], 1) == [0, 1, 0]
+
+
 class _OracleBackedEngine:
     """CPU stand-in for b2ip.Engine in the Indexer host-logic test (tests only): keeps the rows
     in the storage type it was created with and answers searches with the oracle."""
@@ -416,6 +455,56 @@ def test_indexer_host_logic_with_a_stand_in_engine(tmp_path, built, monkeypatch)
     assert small.search_knn(np.zeros((0, d), np.float32), 5) == []
     with pytest.raises(NotImplementedError):
         bi.Indexer(d, 8, 8)
+
+
+def test_hostmap_builds_the_reference_result_objects(built):
+    """csrc/hostmap.c against the reference comprehension it replaces (src/index.py:44-45):
+    same strings (identity for exact `str` ids, `str(x)` otherwise), negative rows index from
+    the end like a Python list, out-of-range rows raise IndexError, score rows are passed through."""
+    hm = built.load_hostmap()
+    rng = np.random.default_rng(5)
+    for ids in ([f"doc{i}" for i in range(1000)], list(range(1000)), [f"d{i}" if i % 2 else i for i in range(1000)]):
+        I = rng.integers(-3, 1000, size=(37, 11), dtype=np.int64)
+        D = rng.random((37, 11), dtype=np.float32)
+        want = [([str(ids[i]) for i in row], D[j]) for j, row in enumerate(I)]
+        got = hm.map_ids(ids, I, 37, 11, list(D))
+        assert len(got) == 37 and all(isinstance(t, tuple) and len(t) == 2 for t in got)
+        assert [g[0] for g in got] == [w[0] for w in want]
+        assert all(type(x) is str for g in got for x in g[0])
+        assert all(np.array_equal(g[1], w[1]) and g[1].base is D for g, w in zip(got, want))
+        if isinstance(ids[int(I[0, 0])], str):
+            assert got[0][0][0] is ids[int(I[0, 0])]                 # no copy of an exact str
+        assert hm.map_ids(ids, I, 37, 11, None) == [w[0] for w in want]
+    with pytest.raises(IndexError):
+        hm.map_ids(["a", "b"], np.array([[0, 2]], dtype=np.int64), 1, 2, None)
+    with pytest.raises(IndexError):
+        hm.map_ids([], np.array([[-1]], dtype=np.int64), 1, 1, None)          # reference: [][-1]
+    with pytest.raises(ValueError):
+        hm.map_ids(["a"], np.zeros((2, 2), dtype=np.int32), 2, 2, None)       # not int64[nq*k]
+    assert hm.map_ids(["a"], np.zeros((0, 4), dtype=np.int64), 0, 4, []) == []
+
+
+def test_search_knn_chunk_pipeline_equals_one_search(built, monkeypatch):
+    """search_knn searches in chunks on a background thread and maps ids chunk by chunk: any
+    chunk size gives the result of one whole search, for numpy and (CPU) torch queries."""
+    import torch
+    from oracle import flatip_oracle as fo
+    import b2ip.indexer as bi
+    monkeypatch.setattr(bi, "Engine", _OracleBackedEngine)
+    d = 16
+    x, q = synth(400, d, 11), synth(23, d, 12)
+    ours, ref = bi.Indexer(d, 0, 8, device=0, store="f32"), fo.OracleIndexer(d, 0, 8)
+    for idx in (ours, ref):
+        idx.index_data([f"p{i}" for i in range(400)], x)
+    want = ref.search_knn(q, 9)
+    for chunk in (1, 5, 23, 1000):
+        ours.knn_chunk = chunk
+        for qq in (q, q.astype(np.float64), torch.from_numpy(q)):
+            got = ours.search_knn(qq, 9)
+            assert len(got) == 23
+            for (gi, gs), (wi, ws) in zip(got, want):
+                # (the stand-in engine's BLAS blocking depends on the chunk size: last-bit noise)
+                assert gi == wi and np.allclose(gs, ws, rtol=1e-6, atol=0) and gs.dtype == np.float32
 
 
 def test_iter_batches_properties(built):
