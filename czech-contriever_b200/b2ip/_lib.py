@@ -21,7 +21,8 @@ MAX_K = 2048
 # every symbol include/b2ip.h declares (tests check the .so exports all of them)
 SYMBOLS = (
     "b2ip_create", "b2ip_create_ex", "b2ip_destroy", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_ntotal",
-    "b2ip_dim", "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_ex", "b2ip_search_exchange", "b2ip_enable_peer_access", "b2ip_merge_topk", "b2ip_merge_topk_strided", "b2ip_export_rows",
+    "b2ip_dim", "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_ex", "b2ip_search_exchange", "b2ip_enable_peer_access", "b2ip_group_create", "b2ip_group_destroy", "b2ip_group_search", "b2ip_group_last_error",
+    "b2ip_merge_topk", "b2ip_merge_topk_strided", "b2ip_export_rows",
     "b2ip_copy_to_device", "b2ip_copy_to_host", "b2ip_stats", "b2ip_last_error", "b2ip_debug_coarse_scores", "b2ip_version",
 )
 
@@ -38,6 +39,7 @@ class Stats(ctypes.Structure):
         ("slabs", ctypes.c_int32), ("query_batches", ctypes.c_int32),
         ("refresh_ms", ctypes.c_float), ("finalize_ms", ctypes.c_float),
         ("max_err_over_eps", ctypes.c_double), ("bound_violations", ctypes.c_int64),
+        ("graph_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
     def as_dict(self) -> dict:
@@ -96,6 +98,14 @@ def load() -> ctypes.CDLL:
     lib.b2ip_search_exchange.argtypes = [vp, i64, vp, i32, ctypes.POINTER(Exchange), ctypes.c_uint32, vp, vp,
                                          ctypes.POINTER(ctypes.c_int64)]
     lib.b2ip_enable_peer_access.argtypes = [vp, i32]
+    lib.b2ip_group_create.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    lib.b2ip_group_create.restype = i32
+    lib.b2ip_group_destroy.argtypes = [vp]
+    lib.b2ip_group_destroy.restype = None
+    lib.b2ip_group_search.argtypes = [vp, i64, vp, i32, i32, vp, vp, ctypes.POINTER(ctypes.c_int64)]
+    lib.b2ip_group_search.restype = i32
+    lib.b2ip_group_last_error.argtypes = [vp]
+    lib.b2ip_group_last_error.restype = ctypes.c_char_p
     lib.b2ip_merge_topk.argtypes = [i32, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.b2ip_merge_topk_strided.argtypes = [i32, vp, i64, i32, i32, vp, vp, i64, i64, vp, vp]
     lib.b2ip_export_rows.argtypes = [vp, i64, i64, vp, i32]

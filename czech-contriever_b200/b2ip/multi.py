@@ -116,9 +116,14 @@ class MultiGpuEngine:
         self._x_ok = None if os.environ.get("B2IP_PEER_EXCHANGE", "1") != "0" else False
         self._x_ex, self._x_bufs, self._x_slot, self._x_thr_cap, self._x_seq = None, None, 0, 0, 0
         self.exchange_searches = 0
+        self._group, self._group_ok = None, (None if os.environ.get("B2IP_PEER_EXCHANGE", "1") != "0" else False)
 
     # -- lifetime / configuration ----------------------------------------------------
     def close(self) -> None:
+        if getattr(self, "_group", None) is not None:
+            from ._lib import load
+            load().b2ip_group_destroy(self._group)
+            self._group = None
         for e in getattr(self, "engines", []):
             e.close()
         if getattr(self, "_pool", None) is not None:
@@ -206,6 +211,11 @@ class MultiGpuEngine:
         from ._lib import GATHER_OWNER, B2ipError, Exchange
         torch = self._torch
         G = len(self.engines)
+        if self._x_ok is None and len(set(self.devices)) != len(self.devices):
+            # shards that share a GPU cannot wait for each other inside kernels (the waiting CTAs
+            # could keep the peer's kernels off the SMs): copy-and-merge path
+            self._x_ok = False
+            return None
         if self._x_ok is None:
             try:
                 for a in range(G):
@@ -240,6 +250,33 @@ class MultiGpuEngine:
             exs.append(pair)
         self._x_bufs, self._x_slot, self._x_thr_cap, self._x_ex, self._x_seq = bufs, slot, thr_cap, exs, 0
         return exs
+
+    def _group_search(self, q_host: np.ndarray, k: int, host_out):
+        """b2ip_group_search over this engine's handles.  Returns the exchange status (0 = done,
+        > 0 = a candidate list overflowed: repeat shard by shard) or None when the devices cannot
+        reach each other (the group cannot be created)."""
+        import ctypes
+        from ._lib import B2IP_F16, B2IP_F32, B2ipError, load
+        lib = load()
+        if self._group is None:
+            arr = (ctypes.c_void_p * len(self.engines))(*[e._h.value for e in self.engines])
+            grp = ctypes.c_void_p()
+            rc = lib.b2ip_group_create(len(self.engines), arr, ctypes.byref(grp))
+            if rc != 0:
+                self._group_ok = False
+                return None
+            self._group, self._group_ok = grp, True
+        status = ctypes.c_int64(0)
+        D, I = host_out
+        assert D.flags["C_CONTIGUOUS"] and I.flags["C_CONTIGUOUS"] and D.dtype == np.float32 and I.dtype == np.int64
+        rc = lib.b2ip_group_search(self._group, q_host.shape[0], ctypes.c_void_p(q_host.ctypes.data),
+                                   B2IP_F16 if q_host.dtype == np.float16 else B2IP_F32, int(k),
+                                   ctypes.c_void_p(D.ctypes.data), ctypes.c_void_p(I.ctypes.data),
+                                   ctypes.byref(status))
+        if rc != 0:
+            msg = lib.b2ip_group_last_error(self._group)
+            raise B2ipError(rc, msg.decode() if msg else "")
+        return int(status.value)
 
     def _search_exchange_one(self, g: int, q_dev0, k: int, ex, seq: int, host_out, lo: int, hi: int):
         """Device g: fan-in of the queries, search + exchange + merge of the queries it owns, and
@@ -291,7 +328,17 @@ class MultiGpuEngine:
                         torch.empty((0, k), dtype=torch.int64, device=dev0))
             return host_out
         D = I = None
-        ex = self._exchange(nq, k) if (G > 1 and mode != "exact") else None
+        if not is_t and G > 1 and mode != "exact" and self._group_ok is not False:
+            # host queries: ONE native call runs uploads, searches + fused exchange and downloads
+            # of all GPUs on the library's own worker threads (b2ip_group_search)
+            status = self._group_search(q_host, k, host_out)
+            if status == 0:
+                self.exchange_searches += 1
+                self._last_stats = [e.stats() for e in self.engines]
+                return host_out
+            if status is None:                       # no P2P path between the devices
+                pass
+        ex = self._exchange(nq, k) if (G > 1 and mode != "exact" and is_t) else None
         if ex is not None:
             self._x_seq += 1
             per = -(-nq // G)

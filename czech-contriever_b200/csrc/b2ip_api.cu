@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -102,10 +103,48 @@ struct b2ip_index_s {
     int extra_rank[MAX_PEERS - 1] = {};     // rank that owns extra_base[e]
     bool ex_thr = false;                    // global threshold round active for this search
     long long ex_timeout_ns = 600ll * 1000000000ll;   // B2IP_EXCHANGE_TIMEOUT_S
+    // CUDA-graph replay of small-batch searches (fixed slab schedule): see tensor_search
+    int graph = 1;                        // option "graph" / env B2IP_GRAPH
+    int graph_timing = 1;                 // keep the per-kernel event records inside the graph
+    unsigned long long ws_gen = 0;        // bumped when a workspace / row buffer moves
+    unsigned long long opt_gen = 0;       // bumped when an option, stream or row mapping changes
+    DynArgs* dyn_dev = nullptr;
+    DynArgs* dyn_host = nullptr;          // pinned
+    struct GraphEntry {
+        int64_t nq, n; int k, cap;
+        unsigned long long ws_gen, opt_gen;
+        bool has_ex; b2ip_exchange_t ex;
+        cudaGraphExec_t exec;
+        int coarse_launches, total_launches, slabs;
+        double coarse_flops;
+        size_t ev_used;
+        unsigned long long last_use;
+    };
+    std::vector<GraphEntry> graphs;
+    unsigned long long graph_clock = 0;
+    long long graph_replays = 0, graph_captures = 0;
     size_t timing_events = 0;             // event triples of the last tensor search (read by b2ip_stats)
     bool timing_pending = false;
     const void* tmap_x_base = nullptr;
     int64_t tmap_x_rows = -1;
+};
+
+// A set of handles of ONE process (one per GPU) searched together: b2ip_group_search.
+struct b2ip_group_s {
+    std::vector<b2ip_handle> hs;
+    std::vector<char*> buf;               // per device: [2 x n gather slots | 2 x n x thr_cap floats | 2 flag arrays]
+    size_t slot = 0, thr_cap = 0;
+    b2ip_exchange_t ex[2][MAX_PEERS];     // [parity][member]
+    unsigned int seq = 0;
+    std::string err;
+    // one persistent worker thread per member
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, done;
+    std::function<void(int)> job;
+    unsigned long long gen = 0;
+    int left = 0;
+    bool stop = false;
 };
 
 namespace {
@@ -140,6 +179,7 @@ int fail(b2ip_handle h, int code, const char* fmt, ...) {
 int ensure(b2ip_handle h, DevBuf& b, size_t bytes) {
     if (b.bytes >= bytes) return B2IP_OK;
     if (b.p) { CU_TRY(h, cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+    h->ws_gen++;
     size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMalloc(&b.p, want); }
@@ -198,6 +238,7 @@ int grow_rows(b2ip_handle h, int64_t need, bool exact = false) {
     h->x32 = nx32;
     h->x16 = nx16;
     h->cap_rows = ncap;
+    h->ws_gen++;
     return B2IP_OK;
 }
 
@@ -438,10 +479,10 @@ void owner_range(const b2ip_exchange_t* ex, int64_t nq, int64_t* q_lo, int64_t* 
     *q_hi = std::min<int64_t>(*q_lo + *per, nq);
 }
 
-int enqueue_exchange(b2ip_handle h, int64_t nq, int k) {
+int enqueue_exchange(b2ip_handle h, int64_t nq, int k, const DynArgs* dyn = nullptr) {
     const b2ip_exchange_t* ex = h->ex;
     exchange_signal_kernel<<<1, 32, 0, h->stream>>>(peer_flags(ex), h->ex_seq, XF_RESULT, h->gstats,
-                                                    h->ex_prior_overflow);
+                                                    h->ex_prior_overflow, dyn);
     h->stats.total_launches += 1;
     int P = 2;
     while (P < ex->world * k) P <<= 1;
@@ -459,10 +500,10 @@ int enqueue_exchange(b2ip_handle h, int64_t nq, int k) {
             nq, k, ex->world, reinterpret_cast<const float*>(mine + static_cast<size_t>(nq) * k * 8),
             reinterpret_cast<const long long*>(mine), ex->slot_bytes / 4, ex->slot_bytes / 8, h->ex_out_s,
             reinterpret_cast<long long*>(h->ex_out_r), P, static_cast<const unsigned int*>(ex->flags[ex->rank]),
-            h->ex_seq, h->gstats + GS_XSTATUS, q_lo, h->ex_timeout_ns);
+            h->ex_seq, h->gstats + GS_XSTATUS, q_lo, h->ex_timeout_ns, dyn);
     } else {
         exchange_wait_kernel<<<1, 32, 0, h->stream>>>(static_cast<const unsigned int*>(ex->flags[ex->rank]),
-                                                      ex->world, h->ex_seq, h->gstats + GS_XSTATUS, h->ex_timeout_ns);
+                                                      ex->world, h->ex_seq, h->gstats + GS_XSTATUS, h->ex_timeout_ns, dyn);
     }
     h->stats.total_launches += 1;
     return B2IP_OK;
@@ -508,8 +549,73 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
     const bool fuse_refresh = h->fuse_refresh && !thr_round;
     size_t ev_used = 0;
     std::vector<int> fallback;
+
+    // ---- CUDA-graph replay (latency regime) -------------------------------------------------
+    // A small batch runs a FIXED launch sequence (prep, slabs + refreshes, finalize, exchange,
+    // counters D2H) with no host decision in between: it is captured once per shape and replayed
+    // with one cudaGraphLaunch; what differs from call to call travels through DynArgs.
+    bool use_graph = false;
+    {
+        int64_t slab0 = std::min<int64_t>(cap, std::max<int64_t>(1024, 8ll * k)) / TILE_X * TILE_X;
+        use_graph = h->graph && !h->verbose && !h->dbg && nq <= qb && nq <= 2048 && n > slab0;
+    }
+    const DynArgs* dyn = nullptr;
+    b2ip_index_s::GraphEntry* entry = nullptr;
+    bool capturing = false;
+    if (use_graph) {
+        DynArgs da{};
+        da.q32 = q32; da.out_s = d_scores; da.out_r = reinterpret_cast<long long*>(d_rows);
+        da.ex_out_s = h->ex_out_s; da.ex_out_r = reinterpret_cast<long long*>(h->ex_out_r);
+        da.seq = h->ex_seq;
+        *h->dyn_host = da;
+        CU_TRY(h, cudaMemcpyAsync(h->dyn_dev, h->dyn_host, sizeof(DynArgs), cudaMemcpyHostToDevice, h->stream));
+        dyn = h->dyn_dev;
+        for (auto& ge : h->graphs) {
+            if (ge.nq == nq && ge.n == n && ge.k == k && ge.cap == cap && ge.ws_gen == h->ws_gen &&
+                ge.opt_gen == h->opt_gen && ge.has_ex == (h->ex != nullptr) &&
+                (!h->ex || memcmp(&ge.ex, h->ex, sizeof(b2ip_exchange_t)) == 0)) {
+                entry = &ge;
+                break;
+            }
+        }
+        if (entry) {
+            entry->last_use = ++h->graph_clock;
+            h->graph_replays++;
+            CU_TRY(h, cudaGraphLaunch(entry->exec, h->stream));
+            h->stats.query_batches = 1;
+            h->stats.coarse_launches = entry->coarse_launches;
+            h->stats.total_launches = entry->total_launches;
+            h->stats.slabs = entry->slabs;
+            h->stats.coarse_flops = entry->coarse_flops;
+            h->stats.graph_mode = 2;
+            ev_used = entry->ev_used;
+        } else {
+            CU_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            capturing = true;
+        }
+    }
+    // event records: plain outside a graph; inside a capture they become event-record NODES
+    // (cudaEventRecordExternal) so the per-kernel times stay measurable, or are left out
+    auto rec = [&](cudaEvent_t e) -> cudaError_t {
+        if (!capturing) return cudaEventRecord(e, h->stream);
+        if (!h->graph_timing) return cudaSuccess;
+        return cudaEventRecordWithFlags(e, h->stream, cudaEventRecordExternal);
+    };
+    // leaves capture mode on an error path
+    auto abort_capture = [&]() {
+        if (!capturing) return;
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(h->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        capturing = false;
+    };
+#define CAP_TRY(expr) do { cudaError_t cap_e__ = (expr); if (cap_e__ != cudaSuccess) { abort_capture(); CU_TRY(h, cap_e__); } } while (0)
+#define CAP_RC(expr) do { int rc__ = (expr); if (rc__ != B2IP_OK) { abort_capture(); return rc__; } } while (0)
+
     for (int64_t q0 = 0; q0 < nq; q0 += qb) {
         const int nqb = static_cast<int>(std::min<int64_t>(qb, nq - q0));
+        if (!entry) {
         h->stats.query_batches++;
         const float* qptr = q32 + q0 * h->d;
         const int nq_pad = static_cast<int>(pad_q(nqb));
@@ -524,10 +630,10 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
             reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p),
             reinterpret_cast<int*>(h->flags.p), h->sh, nq_pad, h->gstats,
-            dense_first ? static_cast<int>(first_slab) : 0);
+            dense_first ? static_cast<int>(first_slab) : 0, dyn);
         h->stats.total_launches++;
         CUtensorMap tmap_q;
-        RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, TILE_Q));
+        CAP_RC(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, TILE_Q));
         const bool use_pair = h->pair && nqb > TILE_Q && h->sm_count >= 2;
         // small batches: streaming kernel (corpus tile on the M side, resident queries) when the
         // padded batch fits next to at least 4 corpus stages in shared memory
@@ -538,7 +644,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             (static_cast<long long>(MAX_SMEM_OPTIN) - STREAM_MISC_BYTES - static_cast<long long>(q_bytes)) / STREAM_X_STAGE_BYTES));
         const bool use_stream = h->stream_kernel && nqb <= 64 && stream_stages >= 4;
         const size_t stream_smem = static_cast<size_t>(std::max(stream_stages, 0)) * STREAM_X_STAGE_BYTES + q_bytes + STREAM_MISC_BYTES;
-        if (use_stream) RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, nq_s));
+        if (use_stream) CAP_RC(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, nq_s));
 
         CoarseParams cp{};
         cp.num_k_blocks = h->d_pad / KBLOCK_ELEMS;
@@ -585,7 +691,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             const bool last = done + s >= n;
             const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
             cudaEvent_t e0 = get_event(h, ev_used++), e1 = get_event(h, ev_used++);
-            CU_TRY(h, cudaEventRecord(e0, h->stream));
+            CAP_TRY(rec(e0));
             if (use_stream) {
                 const int grid = static_cast<int>(std::min<long long>(cp.x_tiles, h->sm_count));
                 if (nq_s == 32)
@@ -603,7 +709,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
                 coarse_filter_kernel<false><<<grid, COARSE_THREADS, COARSE_SMEM_BYTES, h->stream>>>(
                     tmap_q, tmap_x, cp);
             }
-            CU_TRY(h, cudaEventRecord(e1, h->stream));
+            CAP_TRY(rec(e1));
             // the refresh after the LAST slab is fused into the finalize kernel -- unless this
             // rank owes its peers a bound for the global threshold (it must exist before finalize)
             const bool fused = last && fuse_refresh;
@@ -621,7 +727,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
                     reinterpret_cast<int*>(h->flags.p), h->gstats, pub);
             }
             cudaEvent_t e2 = get_event(h, ev_used++);
-            CU_TRY(h, cudaEventRecord(e2, h->stream));
+            CAP_TRY(rec(e2));
             h->stats.coarse_launches++;
             h->stats.total_launches += fused ? 1 : 2;
             h->stats.slabs++;
@@ -656,10 +762,12 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         }
 
         if (thr_round) {
-            exchange_signal_kernel<<<1, 32, 0, h->stream>>>(peer_flags(h->ex), h->ex_seq, XF_THR, h->gstats, 0);
+            exchange_signal_kernel<<<1, 32, 0, h->stream>>>(peer_flags(h->ex), h->ex_seq, XF_THR, h->gstats, 0, dyn);
             h->stats.total_launches++;
         }
         FinalizeParams fp{};
+        fp.dyn = dyn;
+        fp.dyn_out = h->ex ? 0 : 1;     // exchange: finalize writes the (stable) gather slots
         fp.k = k; fp.cap = cap; fp.d = h->d;
         fp.qlist = nullptr;
         fp.cand = cp.cand;
@@ -705,19 +813,55 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         }
         cudaEvent_t f0 = get_event(h->ev_fin, 2 * (h->stats.query_batches - 1));
         cudaEvent_t f1 = get_event(h->ev_fin, 2 * (h->stats.query_batches - 1) + 1);
-        CU_TRY(h, cudaEventRecord(f0, h->stream));
+        CAP_TRY(rec(f0));
         finalize_kernel<true><<<nqb, SEL_THREADS, fin_smem, h->stream>>>(fp);
-        CU_TRY(h, cudaEventRecord(f1, h->stream));
+        CAP_TRY(rec(f1));
         h->stats.total_launches++;
         // end of the device-side search (re-recorded after the exact fallback, if any): the
         // D2H of the counters below and ONE host synchronisation finish the call
         if (q0 + qb >= nq && h->ex) {
             h->ex_prior_overflow = static_cast<long long>(fallback.size());
-            RC_TRY(enqueue_exchange(h, nq, k));
+            CAP_RC(enqueue_exchange(h, nq, k, dyn));
         }
+        if (capturing) {
+            // the counters' D2H is the graph's last node; instantiate, remember, launch
+            CAP_TRY(cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
+                                    cudaMemcpyDeviceToHost, h->stream));
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+            capturing = false;
+            if (ce != cudaSuccess || !g) { cudaGetLastError(); return fail(h, B2IP_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
+            cudaGraphExec_t exec = nullptr;
+            ce = cudaGraphInstantiate(&exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) { cudaGetLastError(); return fail(h, B2IP_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+            if (h->graphs.size() >= 16) {              // drop the least recently used shape
+                size_t lru = 0;
+                for (size_t i = 1; i < h->graphs.size(); i++)
+                    if (h->graphs[i].last_use < h->graphs[lru].last_use) lru = i;
+                cudaGraphExecDestroy(h->graphs[lru].exec);
+                h->graphs.erase(h->graphs.begin() + static_cast<long>(lru));
+            }
+            b2ip_index_s::GraphEntry ge{};
+            ge.nq = nq; ge.n = n; ge.k = k; ge.cap = cap; ge.ws_gen = h->ws_gen; ge.opt_gen = h->opt_gen;
+            ge.has_ex = h->ex != nullptr;
+            if (h->ex) ge.ex = *h->ex;
+            ge.exec = exec;
+            ge.coarse_launches = h->stats.coarse_launches; ge.total_launches = h->stats.total_launches;
+            ge.slabs = h->stats.slabs; ge.coarse_flops = h->stats.coarse_flops;
+            ge.ev_used = h->graph_timing ? ev_used : 0;
+            ge.last_use = ++h->graph_clock;
+            h->graphs.push_back(ge);
+            h->graph_captures++;
+            h->stats.graph_mode = 1;
+            if (!h->graph_timing) ev_used = 0;
+            CU_TRY(h, cudaGraphLaunch(exec, h->stream));
+        }
+        }   // !entry
         if (q0 + qb >= nq) CU_TRY(h, cudaEventRecord(h->ev_t1, h->stream));
-        CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
-                                  cudaMemcpyDeviceToHost, h->stream));
+        if (!use_graph)
+            CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
+                                      cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
         CU_TRY(h, cudaGetLastError());
         std::vector<int> hflags;
@@ -739,6 +883,8 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         for (int i = 0; i < static_cast<int>(hflags.size()); i++)
             if (hflags[i] & FLAG_OVERFLOW) fallback.push_back(static_cast<int>(q0 + i));
     }
+#undef CAP_TRY
+#undef CAP_RC
     // per-kernel times are read from the recorded event pairs lazily, by b2ip_stats (a dozen
     // cudaEventElapsedTime calls are not free next to a 0.7 ms search)
     h->timing_events = ev_used;
@@ -799,7 +945,7 @@ int search_device(b2ip_handle h, int64_t nq, const float* dq, int k, float* d_sc
                     fill_float_kernel<<<64, 256, 0, h->stream>>>(
                         static_cast<float*>(h->ex->gthr[r]) + static_cast<size_t>(h->ex->rank) * h->ex->thr_stride,
                         nq, -INFINITY);
-                exchange_signal_kernel<<<1, 32, 0, h->stream>>>(peer_flags(h->ex), h->ex_seq, XF_THR, h->gstats, 0);
+                exchange_signal_kernel<<<1, 32, 0, h->stream>>>(peer_flags(h->ex), h->ex_seq, XF_THR, h->gstats, 0, nullptr);
             }
             RC_TRY(enqueue_exchange(h, nq, k));
             CU_TRY(h, cudaMemcpyAsync(h->h_gstats, h->gstats, GS_COUNT * sizeof(long long),
@@ -883,6 +1029,11 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
         cudaMalloc(&h->gstats, GS_COUNT * sizeof(long long)) != cudaSuccess ||
         cudaMallocHost(&h->h_gstats, GS_COUNT * sizeof(long long)) != cudaSuccess)
         return bail(B2IP_ERR_OOM, "allocating index state");
+    if (cudaMalloc(&h->dyn_dev, sizeof(DynArgs)) != cudaSuccess ||
+        cudaMallocHost(&h->dyn_host, sizeof(DynArgs)) != cudaSuccess)
+        return bail(B2IP_ERR_OOM, "allocating index state");
+    if (const char* s = getenv("B2IP_GRAPH")) h->graph = atoi(s);
+    if (const char* s = getenv("B2IP_GRAPH_TIMING")) h->graph_timing = atoi(s);
     cudaMemset(h->norm_stats, 0, 2 * sizeof(unsigned int));
     cudaEventCreate(&h->ev_t0);
     cudaEventCreate(&h->ev_t1);
@@ -933,6 +1084,9 @@ void b2ip_destroy(b2ip_handle h) {
     if (h->norm_stats) cudaFree(h->norm_stats);
     if (h->gstats) cudaFree(h->gstats);
     if (h->h_gstats) cudaFreeHost(h->h_gstats);
+    for (auto& ge : h->graphs) cudaGraphExecDestroy(ge.exec);
+    if (h->dyn_dev) cudaFree(h->dyn_dev);
+    if (h->dyn_host) cudaFreeHost(h->dyn_host);
     delete h->pool;
     for (int b = 0; b < 2; b++) {
         if (h->pin[b]) cudaFreeHost(h->pin[b]);
@@ -949,12 +1103,14 @@ void b2ip_destroy(b2ip_handle h) {
 int b2ip_set_stream(b2ip_handle h, void* cuda_stream) {
     if (!h) return B2IP_ERR_INVALID;
     h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    h->opt_gen++;
     return B2IP_OK;
 }
 
 int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     if (!h || !name) return B2IP_ERR_INVALID;
     const std::string n(name);
+    h->opt_gen++;
     if (n == "gx") h->gx = static_cast<int>(std::max<int64_t>(1, value));
     else if (n == "hint_q") h->hint_q = static_cast<int>(value);
     else if (n == "hint_x") h->hint_x = static_cast<int>(value);
@@ -971,6 +1127,8 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "fuse_refresh") h->fuse_refresh = static_cast<int>(value);
     else if (n == "two_stage") h->two_stage = static_cast<int>(value);
     else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;
+    else if (n == "graph") h->graph = static_cast<int>(value);
+    else if (n == "graph_timing") h->graph_timing = static_cast<int>(value);
     else if (n == "shadow_f16") {
         // operand type of the coarse pass of an fp32-stored index; only before the first row
         if (h->store16) return fail(h, B2IP_ERR_INVALID, "shadow_f16: a 16-bit store fixes the operand type");
@@ -1067,6 +1225,7 @@ int b2ip_dim(b2ip_handle h) { return h ? h->d : -1; }
 
 int b2ip_set_row_offset(b2ip_handle h, int64_t offset) {
     if (!h || offset < 0) return B2IP_ERR_INVALID;
+    h->opt_gen++;
     h->row_offset = offset;
     return B2IP_OK;
 }
@@ -1094,6 +1253,7 @@ int b2ip_set_row_segments(b2ip_handle h, int n_segments, const int64_t* local_st
         CU_TRY(h, cudaStreamSynchronize(h->stream));
     }
     h->n_seg = n_segments;
+    h->opt_gen++;
     return B2IP_OK;
 }
 
@@ -1164,7 +1324,7 @@ int b2ip_search_exchange(b2ip_handle h, int64_t nq, const float* queries_dev, in
                          const b2ip_exchange_t* ex, uint32_t seq, float* out_scores_dev,
                          int64_t* out_rows_dev, int64_t* status) {
     if (!h) return B2IP_ERR_INVALID;
-    if (!ex || !status || nq <= 0 || !queries_dev || !out_scores_dev || !out_rows_dev)
+    if (!ex || !status || nq <= 0 || !queries_dev)
         return fail(h, B2IP_ERR_INVALID, "b2ip_search_exchange: NULL argument or nq=%lld", (long long)nq);
     if (k < 1 || k > B2IP_MAX_K) return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_search_exchange: k=%d", k);
     if (ex->world < 1 || ex->world > B2IP_MAX_PEERS || ex->rank < 0 || ex->rank >= ex->world)
@@ -1177,6 +1337,12 @@ int b2ip_search_exchange(b2ip_handle h, int64_t nq, const float* queries_dev, in
     char* mine = static_cast<char*>(ex->gather[ex->rank]) + static_cast<size_t>(ex->rank) * ex->slot_bytes;
     if (ex->gather_mode != B2IP_GATHER_ALL && ex->gather_mode != B2IP_GATHER_OWNER)
         return fail(h, B2IP_ERR_INVALID, "b2ip_search_exchange: gather_mode=%d", ex->gather_mode);
+    {   // the output buffers may be NULL only when this rank owns no query of the search
+        int64_t q_lo = 0, q_hi = nq, per = 0;
+        if (ex->gather_mode == B2IP_GATHER_OWNER) owner_range(ex, nq, &q_lo, &q_hi, &per);
+        if (q_hi > q_lo && (!out_scores_dev || !out_rows_dev))
+            return fail(h, B2IP_ERR_INVALID, "b2ip_search_exchange: NULL output buffer");
+    }
     h->n_extra = 0;
     for (int p = 0; p < ex->world; p++)
         if (p != ex->rank) {
@@ -1199,6 +1365,177 @@ int b2ip_search_exchange(b2ip_handle h, int64_t nq, const float* queries_dev, in
                     "(B2IP_EXCHANGE_TIMEOUT_S): the peer is gone or stuck; this rank's view of the "
                     "exchange is no longer consistent with its peers -- tear the process group down",
                     seq, h->ex_timeout_ns * 1e-9);
+    return B2IP_OK;
+}
+
+namespace {
+constexpr size_t GROUP_FLAG_BYTES = 256;
+
+void group_run(b2ip_group g, std::function<void(int)> f) {
+    std::unique_lock<std::mutex> l(g->m);
+    g->job = std::move(f);
+    g->left = static_cast<int>(g->hs.size());
+    g->gen++;
+    g->cv.notify_all();
+    g->done.wait(l, [g] { return g->left == 0; });
+}
+
+void group_worker(b2ip_group g, int i) {
+    unsigned long long seen = 0;
+    std::unique_lock<std::mutex> l(g->m);
+    for (;;) {
+        g->cv.wait(l, [&] { return g->gen != seen || g->stop; });
+        if (g->stop) return;
+        seen = g->gen;
+        std::function<void(int)> f = g->job;
+        l.unlock();
+        f(i);
+        l.lock();
+        if (--g->left == 0) g->done.notify_one();
+    }
+}
+
+void group_free_buffers(b2ip_group g) {
+    for (size_t i = 0; i < g->buf.size(); i++)
+        if (g->buf[i]) { Guard gd(g->hs[i]->device); cudaFree(g->buf[i]); g->buf[i] = nullptr; }
+}
+
+// (re)allocates the exchange buffers for searches of up to nq queries and k results
+int group_buffers(b2ip_group g, int64_t nq, int k) {
+    const size_t need = (static_cast<size_t>(nq) * k * 12 + 15) / 16 * 16;
+    if (!g->buf.empty() && g->buf[0] && need <= g->slot && static_cast<size_t>(nq) <= g->thr_cap) return B2IP_OK;
+    const int G = static_cast<int>(g->hs.size());
+    const size_t slot = std::max<size_t>(std::max<size_t>(1 << 16, (need + need / 4 + 65535) / 65536 * 65536), g->slot);
+    const size_t thr_cap = std::max<size_t>((static_cast<size_t>(nq) + nq / 4 + 1023) / 1024 * 1024, g->thr_cap);
+    const size_t thr_bytes = static_cast<size_t>(G) * thr_cap * 4;
+    const size_t total = 2 * G * slot + 2 * thr_bytes + 2 * GROUP_FLAG_BYTES;
+    for (int i = 0; i < G; i++) { Guard gd(g->hs[i]->device); cudaStreamSynchronize(g->hs[i]->stream); }
+    group_free_buffers(g);
+    g->buf.assign(G, nullptr);
+    for (int i = 0; i < G; i++) {
+        Guard gd(g->hs[i]->device);
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, total);
+        if (e == cudaSuccess) e = cudaMemset(p, 0, total);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            g->err = std::string("group exchange buffers: ") + cudaGetErrorString(e);
+            group_free_buffers(g);
+            return e == cudaErrorMemoryAllocation ? B2IP_ERR_OOM : B2IP_ERR_CUDA;
+        }
+        g->buf[i] = static_cast<char*>(p);
+    }
+    for (int parity = 0; parity < 2; parity++)
+        for (int i = 0; i < G; i++) {
+            b2ip_exchange_t& ex = g->ex[parity][i];
+            memset(&ex, 0, sizeof(ex));
+            ex.world = G; ex.rank = i; ex.slot_bytes = static_cast<int64_t>(slot);
+            ex.thr_stride = static_cast<int64_t>(thr_cap);
+            ex.gather_mode = B2IP_GATHER_OWNER;
+            for (int p = 0; p < G; p++) {
+                ex.gather[p] = g->buf[p] + parity * G * slot;
+                ex.gthr[p] = g->buf[p] + 2 * G * slot + parity * thr_bytes;
+                ex.flags[p] = g->buf[p] + 2 * G * slot + 2 * thr_bytes + parity * GROUP_FLAG_BYTES;
+            }
+        }
+    g->slot = slot; g->thr_cap = thr_cap; g->seq = 0;
+    return B2IP_OK;
+}
+}  // namespace
+
+int b2ip_group_create(int n_handles, const b2ip_handle* handles, b2ip_group* out) {
+    if (!out) return B2IP_ERR_INVALID;
+    *out = nullptr;
+    if (n_handles < 1 || n_handles > B2IP_MAX_PEERS || !handles)
+        return fail(nullptr, B2IP_ERR_INVALID, "b2ip_group_create: n_handles=%d (1..%d)", n_handles, B2IP_MAX_PEERS);
+    for (int i = 0; i < n_handles; i++) {
+        if (!handles[i]) return fail(nullptr, B2IP_ERR_INVALID, "b2ip_group_create: NULL handle");
+        if (handles[i]->d != handles[0]->d) return fail(nullptr, B2IP_ERR_INVALID, "b2ip_group_create: handles differ in d");
+        for (int j = 0; j < i; j++)
+            if (handles[j]->device == handles[i]->device)
+                return fail(nullptr, B2IP_ERR_INVALID, "b2ip_group_create: two handles on device %d", handles[i]->device);
+    }
+    // every member's kernels store into every other member's buffers
+    for (int i = 0; i < n_handles; i++)
+        for (int j = 0; j < n_handles; j++) {
+            const int rc = b2ip_enable_peer_access(handles[i], handles[j]->device);
+            if (rc != B2IP_OK) return fail(nullptr, rc, "b2ip_group_create: %s", handles[i]->err.c_str());
+        }
+    b2ip_group g = new b2ip_group_s();
+    g->hs.assign(handles, handles + n_handles);
+    for (int i = 0; i < n_handles; i++) g->th.emplace_back(group_worker, g, i);
+    *out = g;
+    return B2IP_OK;
+}
+
+void b2ip_group_destroy(b2ip_group g) {
+    if (!g) return;
+    { std::lock_guard<std::mutex> l(g->m); g->stop = true; }
+    g->cv.notify_all();
+    for (auto& t : g->th) t.join();
+    group_free_buffers(g);
+    delete g;
+}
+
+const char* b2ip_group_last_error(b2ip_group g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+
+int b2ip_group_search(b2ip_group g, int64_t nq, const void* queries_host, int q_dtype, int k,
+                      float* out_scores_host, int64_t* out_rows_host, int64_t* status) {
+    if (!g || !status) return B2IP_ERR_INVALID;
+    *status = 0;
+    if (q_dtype != B2IP_F32 && q_dtype != B2IP_F16) { g->err = "b2ip_group_search: q_dtype"; return B2IP_ERR_INVALID; }
+    if (nq < 0 || (nq > 0 && (!queries_host || !out_scores_host || !out_rows_host)) || k < 1 || k > B2IP_MAX_K) {
+        g->err = "b2ip_group_search: bad arguments";
+        return B2IP_ERR_INVALID;
+    }
+    if (nq == 0) return B2IP_OK;
+    const int rcb = group_buffers(g, nq, k);
+    if (rcb != B2IP_OK) return rcb;
+    const int G = static_cast<int>(g->hs.size());
+    const unsigned int seq = ++g->seq;
+    const int parity = static_cast<int>(seq & 1);
+    const int64_t per = (nq + G - 1) / G;
+    std::vector<int> rcs(G, B2IP_OK);
+    std::vector<int64_t> sts(G, 0);
+    group_run(g, [&](int i) {
+        b2ip_handle h = g->hs[i];
+        Guard gd(h->device);
+        auto run = [&]() -> int {
+            const size_t q_count = static_cast<size_t>(nq) * h->d;
+            const int64_t q_lo = std::min<int64_t>(i * per, nq), q_hi = std::min<int64_t>(q_lo + per, nq);
+            RC_TRY(ensure(h, h->qstage, q_count * sizeof(float)));
+            RC_TRY(ensure(h, h->out_s, static_cast<size_t>(per) * k * sizeof(float)));
+            RC_TRY(ensure(h, h->out_r, static_cast<size_t>(per) * k * sizeof(int64_t)));
+            // every member uploads the queries itself: G host->device copies run in parallel on G links
+            if (q_dtype == B2IP_F16) {
+                RC_TRY(ensure(h, h->qhalf, q_count * 2));
+                RC_TRY(host_to_device(h, h->qhalf.p, queries_host, q_count * 2));
+                const int grid = static_cast<int>(std::min<size_t>((q_count / 2 + 255) / 256 + 1, 65535));
+                widen_f16_kernel<<<grid, 256, 0, h->stream>>>(static_cast<const __half*>(h->qhalf.p),
+                                                              static_cast<float*>(h->qstage.p),
+                                                              static_cast<long long>(q_count));
+            } else {
+                RC_TRY(host_to_device(h, h->qstage.p, queries_host, q_count * sizeof(float)));
+            }
+            RC_TRY(b2ip_search_exchange(h, nq, static_cast<const float*>(h->qstage.p), k, &g->ex[parity][i], seq,
+                                        static_cast<float*>(h->out_s.p), static_cast<int64_t*>(h->out_r.p), &sts[i]));
+            if (sts[i] == 0 && q_hi > q_lo) {
+                // this member's slice of the answer leaves on its own copy engine
+                RC_TRY(device_to_host(h, out_scores_host + q_lo * k, h->out_s.p, static_cast<size_t>(q_hi - q_lo) * k * sizeof(float)));
+                RC_TRY(device_to_host(h, out_rows_host + q_lo * k, h->out_r.p, static_cast<size_t>(q_hi - q_lo) * k * sizeof(int64_t)));
+            }
+            return B2IP_OK;
+        };
+        rcs[i] = run();
+    });
+    for (int i = 0; i < G; i++) {
+        if (rcs[i] != B2IP_OK) {
+            g->err = "member " + std::to_string(i) + ": " + g->hs[i]->err;
+            return rcs[i];
+        }
+        *status = std::max(*status, sts[i]);
+    }
     return B2IP_OK;
 }
 
@@ -1238,7 +1575,7 @@ int b2ip_merge_topk_strided(int device, void* cuda_stream, int64_t nq, int k, in
     if (e == cudaSuccess) {
         merge_topk_kernel<<<static_cast<unsigned int>(nq), SEL_THREADS, smem, st>>>(
             nq, k, n_lists, scores, reinterpret_cast<const long long*>(rows), scores_list_stride,
-            rows_list_stride, out_scores, reinterpret_cast<long long*>(out_rows), P, nullptr, 0u, nullptr, 0, 0);
+            rows_list_stride, out_scores, reinterpret_cast<long long*>(out_rows), P, nullptr, 0u, nullptr, 0, 0, nullptr);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1328,7 +1665,7 @@ int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev
         queries_dev, reinterpret_cast<__nv_bfloat16*>(h->q16.p), static_cast<int>(nq), h->d, h->d_pad,
         h->norm_stats, reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
         reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p), reinterpret_cast<int*>(h->flags.p), h->sh,
-        static_cast<int>(pad_q(nq)), nullptr, 0);
+        static_cast<int>(pad_q(nq)), nullptr, 0, nullptr);
     CUtensorMap tmap_q, tmap_x;
     RC_TRY(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nq), h->d_pad, TILE_Q));
     RC_TRY(make_tmap_bf16(h, &tmap_x, h->x16, h->n, h->d_pad, TILE_X));

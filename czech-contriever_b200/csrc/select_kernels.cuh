@@ -68,6 +68,21 @@ __device__ __forceinline__ void wait_peer_flags(const unsigned int* flags, int w
     __syncthreads();
 }
 
+// Per-call values of a search whose launch sequence is replayed from a CUDA graph (small query
+// batches): the graph's kernel nodes keep their baked parameters and read what changes from one
+// call to the next -- caller buffers, exchange sequence number -- from this device-resident block,
+// which the host refreshes with one small copy ahead of the graph launch.  nullptr = use the
+// kernel's own parameters.
+struct DynArgs {
+    const float* q32;        // caller's fp32 queries
+    float* out_s;            // caller's result buffers (plain search)
+    long long* out_r;
+    float* ex_out_s;         // merged results of the peer-direct exchange
+    long long* ex_out_r;
+    unsigned int seq;        // exchange sequence number
+    unsigned int pad;
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -239,7 +254,9 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
                                     float* __restrict__ eps2, float* __restrict__ thr,
                                     int* __restrict__ cnt, int* __restrict__ kept,
                                     int* __restrict__ flags, int sh, int nq_pad,
-                                    long long* __restrict__ gstats, int init_cnt) {
+                                    long long* __restrict__ gstats, int init_cnt,
+                                    const DynArgs* __restrict__ dyn) {
+    if (dyn) q32 = dyn->q32;
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x < GS_COUNT && gstats) gstats[threadIdx.x] = 0;
@@ -577,6 +594,8 @@ struct FinalizeParams {
     unsigned int g_seq;
     long long g_timeout_ns;
     long long* gstats;
+    const DynArgs* dyn;               // graph replay: q32 / g_seq (and, with dyn_out, the output buffers) come from here
+    int dyn_out;
 };
 
 __device__ void block_bitonic_desc(unsigned long long* s, int P) {
@@ -595,7 +614,13 @@ __device__ void block_bitonic_desc(unsigned long long* s, int P) {
 }
 
 template <bool kRescore>
-__global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizeParams p) {
+__global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizeParams p0) {
+    FinalizeParams p = p0;
+    if (p.dyn) {
+        p.q32 = p.dyn->q32;
+        p.g_seq = p.dyn->seq;
+        if (p.dyn_out) { p.out_scores = p.dyn->out_s; p.out_rows = p.dyn->out_r; }
+    }
     extern __shared__ __align__(16) uint8_t fsm[];
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(fsm);   // [SORT_CAP]
     // the query, widened to fp64 ONCE: the rescore is bound by F2F.F64.F32 conversions (16 per
@@ -939,7 +964,9 @@ struct PeerFlags {
 // the flag.  word = XF_RESULT (after finalize; also publishes the overflow count) or XF_THR
 // (after the last refresh).
 __global__ void exchange_signal_kernel(PeerFlags pf, unsigned int seq, int word,
-                                       const long long* __restrict__ gstats, long long prior_overflow) {
+                                       const long long* __restrict__ gstats, long long prior_overflow,
+                                       const DynArgs* __restrict__ dyn) {
+    if (dyn) seq = dyn->seq;
     const int p = threadIdx.x;
     if (p >= pf.world) return;
     unsigned int* f = pf.flags[p] + XF_WORDS * pf.rank;
@@ -954,7 +981,9 @@ __global__ void exchange_signal_kernel(PeerFlags pf, unsigned int seq, int word,
 // A rank that owns no query of a search (owner mode, nq < world) has nothing to merge but still
 // reports the exchange status (overflows, timeouts) like everyone else.
 __global__ void exchange_wait_kernel(const unsigned int* wait_flags, int world, unsigned int seq,
-                                     long long* __restrict__ xstatus, long long timeout_ns) {
+                                     long long* __restrict__ xstatus, long long timeout_ns,
+                                     const DynArgs* __restrict__ dyn) {
+    if (dyn) seq = dyn->seq;
     wait_peer_flags(wait_flags, world, XF_RESULT, seq, timeout_ns, xstatus);
     if (threadIdx.x == 0) {
         long long ov = 0;
@@ -982,7 +1011,12 @@ merge_topk_kernel(long long nq, int k, int n_lists, const float* __restrict__ sc
                   long long rows_list_stride, float* __restrict__ out_scores,
                   long long* __restrict__ out_rows, int P, const unsigned int* wait_flags,
                   unsigned int seq, long long* __restrict__ xstatus, long long q_first,
-                  long long timeout_ns) {
+                  long long timeout_ns, const DynArgs* __restrict__ dyn) {
+    if (dyn) {
+        seq = dyn->seq;
+        out_scores = dyn->ex_out_s;
+        out_rows = dyn->ex_out_r;
+    }
     extern __shared__ __align__(16) uint8_t msm[];
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(msm);
     // owner mode: this rank merges queries [q_first, q_first + gridDim.x) of the search and

@@ -83,6 +83,10 @@ typedef struct b2ip_stats_s {
      * search rescored, max |coarse - exact| / eps_q (must stay < 1) and the number of rows above 1 */
     double max_err_over_eps;
     int64_t bound_violations;
+    /* small batches replay their fixed launch sequence from a CUDA graph: 0 = plain launches,
+     * 1 = captured by this call, 2 = replayed */
+    int32_t graph_mode;
+    int32_t reserved;
 } b2ip_stats_t;
 
 /* replaces faiss.IndexFlatIP(vector_sz)                       -- src/index.py:21
@@ -103,7 +107,9 @@ int b2ip_set_stream(b2ip_handle h, void* cuda_stream);
  * L2 eviction priority of the query / corpus TMA streams (0 normal, 1 first, 2 last),
  * "cand_budget_mb" device memory allowed for candidate lists (sets the query batch),
  * "shadow_f16" (B2IP_STORE_F32 only, before the first add): 1 = fp16 operands for the coarse
- * pass instead of bf16 (tighter error bound, saturating at +-65504), "pair" 0/1 CTA-pair kernel. */
+ * pass instead of bf16 (tighter error bound, saturating at +-65504), "pair" 0/1 CTA-pair kernel,
+ * "graph" 0/1 CUDA-graph replay of small-batch searches (env B2IP_GRAPH), "graph_timing" 0/1 keep
+ * the per-kernel event records inside the graph (b2ip_stats' coarse_ms etc.). */
 int b2ip_set_option(b2ip_handle h, const char* name, int64_t value);
 
 /* Optional capacity hint before a series of b2ip_add calls (avoids regrowth copies). */
@@ -208,6 +214,23 @@ int b2ip_search_exchange(b2ip_handle h, int64_t nq, const float* queries_dev, in
  * so b2ip_search_exchange can be used between handles of the same process with plain device
  * pointers in b2ip_exchange_t.  Fails with B2IP_ERR_UNSUPPORTED when the devices have no P2P path. */
 int b2ip_enable_peer_access(b2ip_handle h, int peer_device);
+
+/* The row-sharded search of ONE process over several handles (one per GPU, each holding a row
+ * shard whose ids are made global with b2ip_set_row_offset / b2ip_set_row_segments): what the
+ * reference's single-process driver (passage_retrieval.py never starts torch.distributed) needs to
+ * use a whole multi-GPU box.  b2ip_group_search takes HOST queries ([nq,d] fp32 or fp16) and fills
+ * HOST results ([nq,k]); inside, one worker thread per member uploads the queries, runs
+ * b2ip_search_exchange (global threshold, owner mode) against library-owned peer buffers and
+ * downloads the slice of queries its GPU owns -- uploads, searches and downloads of all members
+ * overlap, no Python in between.  *status != 0: a candidate list overflowed somewhere, the output
+ * is not valid and the caller repeats the search member by member (b2ip_search + b2ip_merge_topk).
+ * The handles must outlive the group; a group is not re-entrant. */
+typedef struct b2ip_group_s* b2ip_group;
+int b2ip_group_create(int n_handles, const b2ip_handle* handles, b2ip_group* out);
+void b2ip_group_destroy(b2ip_group g);
+int b2ip_group_search(b2ip_group g, int64_t nq, const void* queries_host, int q_dtype, int k,
+                      float* out_scores_host, int64_t* out_rows_host, int64_t* status);
+const char* b2ip_group_last_error(b2ip_group g);
 
 /* replaces faiss.write_index's read of the stored vectors       -- src/index.py:53
  * Copies rows [row0, row0+n) as fp32 into out ([n,d]). */

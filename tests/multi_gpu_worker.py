@@ -3,6 +3,8 @@ single-GPU search bit for bit (same kernels, merge keeps score desc / lower glob
 import os
 import sys
 
+os.environ.setdefault("B2IP_EXCHANGE_TIMEOUT_S", "60")     # a lost flag fails the test in a minute, not ten
+
 import numpy as np
 import torch
 import torch.distributed as dist

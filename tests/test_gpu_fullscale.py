@@ -39,6 +39,43 @@ def full_index():
     e.close()
 
 
+def _fp64_topk(torch, qs64, rows_iter, k, dev):
+    """Exact fp64 top-k of qs64 [m,d] over all rows produced by rows_iter (the whole corpus)."""
+    m = qs64.shape[0]
+    best_s = torch.full((m, 0), 0.0, dtype=torch.float64, device=dev)
+    best_i = torch.zeros((m, 0), dtype=torch.int64, device=dev)
+    for g0, rows in rows_iter:
+        s = qs64 @ rows.double().T
+        ids = torch.arange(g0, g0 + rows.shape[0], device=dev).expand(m, -1)
+        cs, ci = torch.cat([best_s, s], dim=1), torch.cat([best_i, ids], dim=1)
+        top = torch.topk(cs, k, dim=1)
+        best_s, best_i = top.values, torch.gather(ci, 1, top.indices)
+        del s, cs, ci
+    return best_s, best_i
+
+
+def _assert_matches_fp64(torch, ours_s, ours_i, best_s, best_i, label):
+    """north_star acceptance against the fp64 truth: scores within 1e-5 relative, identical id
+    sets except for ties within 1e-5 relative of the k-th score."""
+    rel = (ours_s.double() - best_s).abs() / best_s.abs().clamp_min(1e-30)
+    assert float(rel.max()) <= RTOL, f"{label}: score error {float(rel.max()):.3e} relative"
+    oi, bi, os_, bs = ours_i.cpu(), best_i.cpu(), ours_s.double().cpu(), best_s.cpu()
+    swaps = 0
+    for j in range(oi.shape[0]):
+        a, b = set(oi[j].tolist()), set(bi[j].tolist())
+        if a == b:
+            continue
+        swaps += 1
+        kth = float(bs[j, -1])
+        for r in a - b:           # ids on one side only must tie with the k-th score
+            sc = float(os_[j][oi[j] == r][0])
+            assert abs(sc - kth) <= RTOL * abs(kth), f"{label} query {j}: row {r} score {sc} vs k-th {kth}"
+        for r in b - a:
+            sc = float(bs[j][bi[j] == r][0])
+            assert abs(sc - kth) <= RTOL * abs(kth), f"{label} query {j}: missing row {r} score {sc} vs k-th {kth}"
+    return swaps
+
+
 def test_c3_full_scale_properties_and_fp64_subset(full_index):
     import torch
     e, gen_rows, dev = full_index
@@ -52,6 +89,8 @@ def test_c3_full_scale_properties_and_fp64_subset(full_index):
     Dg, Ig = e.search(queries, K)
     st = e.stats()
     assert st["coarse_launches"] >= 2 and st["fallback_queries"] == 0
+    # run-time certificate of the coarse pass's error bound over every rescored row
+    assert st["bound_violations"] == 0 and 0.0 < st["max_err_over_eps"] < 1.0, st
     # (a) properties
     assert bool((Dg[:, 1:] <= Dg[:, :-1]).all()), "rows must be score-descending"
     assert int(Ig.min()) >= 0 and int(Ig.max()) < N
@@ -61,41 +100,51 @@ def test_c3_full_scale_properties_and_fp64_subset(full_index):
     assert np.array_equal(top1, own), "a stored row used as the query must be its own best match"
     self_scores = (q_own.double() * q_own.double()).sum(dim=1)
     assert torch.allclose(Dg[2048:, 0].double(), self_scores, rtol=RTOL, atol=0)
-    # (b) fp64 brute force over all 21M rows for 48 of the queries (32 random + 16 stored rows)
-    sel = torch.cat([torch.arange(0, 32, device=dev), torch.arange(2048, 2064, device=dev)])
-    qs = queries[sel].double()
-    best_s = torch.full((len(sel), 0), 0.0, dtype=torch.float64, device=dev)
-    best_i = torch.zeros((len(sel), 0), dtype=torch.int64, device=dev)
-    for g0, rows in gen_rows(torch, 0, N, D, 1234, dev):
-        s = qs @ rows.double().T
-        ids = torch.arange(g0, g0 + rows.shape[0], device=dev).expand(len(sel), -1)
-        cs, ci = torch.cat([best_s, s], dim=1), torch.cat([best_i, ids], dim=1)
-        top = torch.topk(cs, K, dim=1)
-        best_s, best_i = top.values, torch.gather(ci, 1, top.indices)
-    ours_s, ours_i = Dg[sel].double(), Ig[sel]
-    rel = (ours_s - best_s).abs() / best_s.abs().clamp_min(1e-30)
-    assert float(rel.max()) <= RTOL, f"score error {float(rel.max()):.3e} relative"
-    for j in range(len(sel)):
-        a, b = set(ours_i[j].tolist()), set(best_i[j].tolist())
-        if a == b:
-            continue
-        kth = float(best_s[j, -1])
-        for r in a ^ b:           # ids on one side only must tie with the k-th score
-            x = torch.from_numpy(e.export_rows(int(r), 1)).to(dev).double()[0]
-            sc = float(qs[j] @ x)
-            assert abs(sc - kth) <= RTOL * abs(kth), f"query {j}: row {r} score {sc} vs k-th {kth}"
+    # (b) fp64 brute force over all 21M rows for 1,024 + 64 of the queries (>= 1,000)
+    sel = torch.cat([torch.arange(0, 1024, device=dev), torch.arange(2048, 2112, device=dev)])
+    best_s, best_i = _fp64_topk(torch, queries[sel].double(), gen_rows(torch, 0, N, D, 1234, dev), K, dev)
+    _assert_matches_fp64(torch, Dg[sel], Ig[sel], best_s, best_i, "C3")
 
 
-def test_c5_small_batches_on_the_full_corpus_match_the_large_batch(full_index):
-    """Latency regime (config 5: batches of 1-64, k = 10) over all 21M rows: the fixed-schedule
-    single-tile path must return exactly what the large-batch path returns for the same queries."""
+def test_c5_small_batches_on_the_full_corpus(full_index):
+    """Latency regime (config 5: batches of 1-64, k = 10) over all 21M rows, against the fp64
+    brute force (not against another CUDA path); the fixed-schedule streaming path must also
+    return exactly what the large-batch path returns for the same queries."""
     import torch
-    e, _, dev = full_index
+    e, gen_rows, dev = full_index
     gen = torch.Generator(device=dev).manual_seed(99)
     q = torch.randn((4096, D), generator=gen, device=dev)
     q /= q.norm(dim=1, keepdim=True)
     Dl, Il = e.search(q, 10)                       # adaptive schedule, CTA-pair kernel
+    best_s, best_i = _fp64_topk(torch, q[:64].double(), gen_rows(torch, 0, N, D, 1234, dev), 10, dev)
     for b in (1, 7, 64):
-        Ds, Is = e.search(q[:b].contiguous(), 10)  # fixed schedule, single-CTA kernel
-        assert e.stats()["fallback_queries"] == 0
-        assert torch.equal(Is, Il[:b]) and torch.equal(Ds, Dl[:b])
+        for rep in range(2):                       # second call replays the CUDA graph
+            Ds, Is = e.search(q[:b].contiguous(), 10)  # fixed schedule, streaming kernel
+            st = e.stats()
+            assert st["fallback_queries"] == 0 and st["bound_violations"] == 0
+            assert st["graph_mode"] == (1 if rep == 0 else 2)
+            assert torch.equal(Is, Il[:b]) and torch.equal(Ds, Dl[:b])
+            _assert_matches_fp64(torch, Ds, Is, best_s[:b], best_i[:b], f"C5 batch {b}")
+
+
+def test_c4_bf16_store_k1000_on_the_full_corpus(full_index):
+    """Config 4 at full size: 21M bf16-STORED rows, k = 1000.  The index is exact w.r.t. the
+    stored (bf16-rounded) values, so the fp64 truth is computed from those ("same inputs")."""
+    import torch
+    from b2ip import Engine
+    _, gen_rows, dev = full_index
+    e4 = Engine(D, 0, store="bf16")
+    e4.reserve(N)
+    for _, rows in gen_rows(torch, 0, N, D, 1234, dev):
+        e4.add(rows)
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    q = torch.randn((1024, D), generator=gen, device=dev)
+    q /= q.norm(dim=1, keepdim=True)
+    Dg, Ig = e4.search(q, 1000)
+    st = e4.stats()
+    assert st["fallback_queries"] == 0 and st["bound_violations"] == 0 and st["max_err_over_eps"] < 1.0, st
+    assert bool((Dg[:, 1:] <= Dg[:, :-1]).all()) and int(Ig.min()) >= 0 and int(Ig.max()) < N
+    stored = ((g0, rows.bfloat16().float()) for g0, rows in gen_rows(torch, 0, N, D, 1234, dev))
+    best_s, best_i = _fp64_topk(torch, q[:256].double(), stored, 1000, dev)
+    _assert_matches_fp64(torch, Dg[:256], Ig[:256], best_s, best_i, "C4")
+    e4.close()

@@ -93,6 +93,47 @@ def test_small_query_batches_latency_regime(fo, nq, k):
     fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
 
 
+def test_small_batches_replay_a_cuda_graph(fo):
+    """The fixed launch sequence of a small batch is captured once per shape and replayed: the
+    replays must pick up NEW query / output buffers (DynArgs) and give the oracle's answer, for
+    host and device buffers, and per-kernel timings must survive inside the graph."""
+    import torch
+    x = synth(150_000, 768, 77)
+    e = _engine(x)
+    modes = []
+    for it in range(5):
+        q = synth(48, 768, 1000 + it)                      # new queries, new buffers every call
+        D, I = e.search(q, 10)
+        st = e.stats()
+        modes.append(st["graph_mode"])
+        assert st["fallback_queries"] == 0 and st["slabs"] >= 2 and st["coarse_launches"] == st["slabs"]
+        Do, Io = fo.search(q, x, 10)
+        fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+        if st["graph_mode"] == 2:
+            assert st["coarse_ms"] > 0 and st["total_ms"] >= st["coarse_ms"]
+    assert modes[0] == 1 and set(modes[1:]) == {2}, modes
+    qd = torch.from_numpy(synth(48, 768, 5)).cuda()
+    outs = []
+    for it in range(3):                                   # device buffers: fresh output tensors per call
+        Dd, Id = e.search(qd, 10)
+        outs.append((Dd, Id))
+    assert all(torch.equal(o[1], outs[0][1]) and torch.equal(o[0], outs[0][0]) for o in outs)
+    Do, Io = fo.search(qd.cpu().numpy(), x, 10)
+    fo.compare_topk(outs[2][0].cpu().numpy(), outs[2][1].cpu().numpy(), Do, Io, qd.cpu().numpy(), x, rtol=RTOL)
+    # rows added after a capture: the old graph must not be replayed for the new corpus size
+    e.add(synth(1000, 768, 78))
+    x2 = np.concatenate([x, synth(1000, 768, 78)])
+    q = synth(48, 768, 2000)
+    D, I = e.search(q, 10)
+    assert e.stats()["graph_mode"] == 1
+    Do, Io = fo.search(q, x2, 10)
+    fo.compare_topk(D, I, Do, Io, q, x2, rtol=RTOL)
+    # graph off: same answer from plain launches
+    e.set_option("graph", 0)
+    D0, I0 = e.search(q, 10)
+    assert e.stats()["graph_mode"] == 0 and np.array_equal(I0, I) and np.array_equal(D0, D)
+
+
 @pytest.mark.parametrize("nq", [8, 3000])
 def test_ascending_scores_overflow_every_list(fo, nq):
     """Adversarial order: rows sorted by increasing score, every row beats the running threshold,

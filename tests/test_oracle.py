@@ -127,3 +127,69 @@ def test_oracle_indexer_restates_reference_indexer(tmp_path):
     iy.deserialize_from(str(tmp_path))
     assert iy.index_id_to_db_id == ix.index_id_to_db_id and np.array_equal(iy.rows, ix.rows)
     assert os.path.getsize(tmp_path / "index.faiss") == 45 + 4 * 30 * 16
+
+
+# ------------------------------------------------------------------------------------------
+# Pins that activate the day `import faiss` works (faiss-cpu==1.8.0, reference environment.yml:138):
+# the restatement, the index.faiss writer / reader and the drop-in's host logic against the REAL
+# library and the REAL reference class.  Skipped in this image (faiss is not installable offline).
+# ------------------------------------------------------------------------------------------
+def test_oracle_backend_is_reported():
+    """Without faiss the oracle says it is a port; with faiss it must say it is the reference."""
+    assert fo.backend_kind() == ("reference" if fo.real_faiss() is not None else "port")
+    assert ("faiss" in fo.backend_description())
+
+
+@pytest.mark.parametrize("n,nq,k,d", [(4000, 50, 100, 768), (4000, 7, 10, 768), (3000, 33, 1, 64),
+                                      (9000, 21, 1000, 128), (50, 5, 100, 32)])
+def test_restatement_matches_real_faiss(n, nq, k, d):
+    faiss = pytest.importorskip("faiss")
+    x, q = synth(n, d, 1234), synth(nq, d, 4321)
+    index = faiss.IndexFlatIP(d)
+    index.add(x)
+    Df, If = index.search(q, k)
+    Dr, Ir = fo.restatement_search(q, x, k)
+    assert np.array_equal(If >= 0, Ir >= 0), "padding pattern (ntotal < k)"
+    fo.compare_topk(Dr, Ir, Df, If, q, x, rtol=1e-5)
+    assert np.array_equal(Df[If < 0], Dr[Ir < 0])            # -FLT_MAX padding scores
+
+
+def test_index_faiss_files_are_interchangeable_with_real_faiss(tmp_path):
+    faiss = pytest.importorskip("faiss")
+    rows = synth(1000, 24, 3)
+    ours, theirs = str(tmp_path / "ours.faiss"), str(tmp_path / "theirs.faiss")
+    fo.write_index_flat_ip(ours, rows)
+    index = faiss.IndexFlatIP(24)
+    index.add(rows)
+    faiss.write_index(index, theirs)
+    assert open(ours, "rb").read() == open(theirs, "rb").read(), "IxFI byte layout"
+    back = faiss.read_index(ours)
+    assert back.ntotal == 1000 and back.d == 24 and back.metric_type == faiss.METRIC_INNER_PRODUCT
+    assert np.array_equal(fo.read_index_flat_ip(theirs), rows)
+    import b2ip
+    d, n, blocks = b2ip.stream_flat_ip_rows(theirs)
+    assert (d, n) == (24, 1000) and np.array_equal(np.concatenate(list(blocks)), rows)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/index.py"), reason="reference checkout not present")
+def test_oracle_indexer_matches_the_real_reference_indexer(tmp_path):
+    """The real reference class (src/index.py, imported from /root/reference) against the
+    restatement OracleIndexer: same ids, scores and files for the same calls."""
+    pytest.importorskip("faiss")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_index", "/root/reference/src/index.py")
+    ref_index = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_index)
+    d = 32
+    a = synth(300, d, 1, normalize=False).astype(np.float16)
+    q = synth(9, d, 4, normalize=False).astype(np.float16)
+    real, ours = ref_index.Indexer(d, 0, 8), fo.OracleIndexer(d, 0, 8)
+    for idx in (real, ours):
+        idx.index_data([f"p{i}" for i in range(300)], a)
+    for (ri, rs), (oi, os_) in zip(real.search_knn(q, 10), ours.search_knn(q, 10)):
+        assert ri == oi and np.allclose(rs, os_, rtol=1e-5, atol=0)
+    da, db = tmp_path / "a", tmp_path / "b"
+    da.mkdir(); db.mkdir()
+    real.serialize(str(da)); ours.serialize(str(db))
+    assert (da / "index.faiss").read_bytes() == (db / "index.faiss").read_bytes()
+    assert (da / "index_meta.faiss").read_bytes() == (db / "index_meta.faiss").read_bytes()
