@@ -58,11 +58,22 @@ class Engine:
     # -- configuration -------------------------------------------------------------
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         """Run on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._torch_stream = None
         check(self._lib.b2ip_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)), self._h)
 
     def use_torch_stream(self) -> None:
         import torch
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        ptr = torch.cuda.current_stream(self.device).cuda_stream
+        self.set_stream(ptr)
+        self._torch_stream = ptr
+
+    def _order_after_torch(self) -> None:
+        """Work the caller queued on torch's current stream must be visible to the engine: nothing
+        to do when the engine runs ON that stream (use_torch_stream), else wait for it."""
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_torch_stream", None) != cur.cuda_stream:
+            cur.synchronize()
 
     def set_option(self, name: str, value: int) -> None:
         check(self._lib.b2ip_set_option(self._h, name.encode(), int(value)), self._h)
@@ -143,7 +154,7 @@ class Engine:
                 I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
             else:
                 D, I = out
-            torch.cuda.current_stream(self.device).synchronize()
+            self._order_after_torch()
             check(self._lib.b2ip_search_ex(self._h, nq, ctypes.c_void_p(q.data_ptr()),
                                            B2IP_F16 if q.dtype == torch.float16 else B2IP_F32, k,
                                            ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
@@ -189,7 +200,7 @@ class Engine:
         D = torch.empty((n_out, k), dtype=torch.float32, device=q.device)
         I = torch.empty((n_out, k), dtype=torch.int64, device=q.device)
         status = ctypes.c_int64(0)
-        torch.cuda.current_stream(self.device).synchronize()
+        self._order_after_torch()
         check(self._lib.b2ip_search_exchange(self._h, nq, ctypes.c_void_p(q.data_ptr()), k, ctypes.byref(ex),
                                              ctypes.c_uint32(seq & 0xFFFFFFFF), ctypes.c_void_p(D.data_ptr()),
                                              ctypes.c_void_p(I.data_ptr()), ctypes.byref(status)), self._h)

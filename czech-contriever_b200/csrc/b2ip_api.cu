@@ -105,7 +105,8 @@ struct b2ip_index_s {
     long long ex_timeout_ns = 600ll * 1000000000ll;   // B2IP_EXCHANGE_TIMEOUT_S
     // CUDA-graph replay of small-batch searches (fixed slab schedule): see tensor_search
     int graph = 1;                        // option "graph" / env B2IP_GRAPH
-    int graph_timing = 1;                 // keep the per-kernel event records inside the graph
+    int graph_timing = 0;                 // keep the per-kernel event records inside the graph (3 us per node:
+                                          // off by default; b2ip_stats then reports total_ms only)
     unsigned long long ws_gen = 0;        // bumped when a workspace / row buffer moves
     unsigned long long opt_gen = 0;       // bumped when an option, stream or row mapping changes
     DynArgs* dyn_dev = nullptr;
@@ -423,7 +424,7 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
     CU_TRY(h, cudaMemcpyAsync(qlist_dev, qlist_host, static_cast<size_t>(nql) * sizeof(int),
                               cudaMemcpyHostToDevice, h->stream));
     const size_t sq_bytes = static_cast<size_t>(EXACT_QB) * h->d * sizeof(float);
-    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(double);
+    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
     const int sgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
     const int hgrid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(h->sm_count) * 4));
     for (int64_t g0 = 0; g0 < nql; g0 += EXACT_QB) {
@@ -531,7 +532,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
     RC_TRY(ensure(h, h->flags, qb * sizeof(int)));
     RC_TRY(ensure(h, h->cand, static_cast<size_t>(qb) * cap * 8));
 
-    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(double);
+    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
     // tensor maps of the corpus are rebuilt only when the rows moved or grew
     if (h->tmap_x_base != h->x16 || h->tmap_x_rows != n) {
         RC_TRY(make_tmap_bf16(h, &h->tmap_x_pair, h->x16, n, h->d_pad, 128));
@@ -1045,7 +1046,7 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     {   // opt-in shared memory sizes, once per process and device
         // (upper bounds for the largest supported d, so handles of different d can coexist)
-        const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(B2IP_MAX_D) * sizeof(double);
+        const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(B2IP_MAX_D) * sizeof(float);
         if (cudaFuncSetAttribute(coarse_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES) != cudaSuccess ||

@@ -20,6 +20,7 @@ constexpr int REFRESH_SMEM_KEYS = 4096;   // candidate lists up to this size are
 static_assert(REFRESH_SMEM_KEYS <= SORT_CAP, "finalize stages the fused refresh in its sort buffer");
 constexpr int FLAG_OVERFLOW = 1;
 constexpr int EXACT_QB = 8;          // queries per pass of the exact path
+constexpr int RESCORE_JU = 8;        // finalize: float4 chunks per lane held in registers per row (d <= 1024)
 
 // device-side counters of one search (int64 each)
 enum { GS_MAX_KEPT = 0, GS_OVERFLOW = 1, GS_CANDIDATES = 2, GS_RESCORED = 3, GS_XSTATUS = 4,
@@ -614,18 +615,16 @@ __device__ void block_bitonic_desc(unsigned long long* s, int P) {
 }
 
 template <bool kRescore>
-__global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizeParams p0) {
-    FinalizeParams p = p0;
-    if (p.dyn) {
-        p.q32 = p.dyn->q32;
-        p.g_seq = p.dyn->seq;
-        if (p.dyn_out) { p.out_scores = p.dyn->out_s; p.out_rows = p.dyn->out_r; }
-    }
+__global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_constant__ FinalizeParams p) {
+    // graph replay: the per-call values come from DynArgs (the parameter block itself stays in
+    // constant memory: no local copy)
+    const float* const q32 = p.dyn ? p.dyn->q32 : p.q32;
+    const unsigned int g_seq = p.dyn ? p.dyn->seq : p.g_seq;
+    float* const out_scores = (p.dyn && p.dyn_out) ? p.dyn->out_s : p.out_scores;
+    long long* const out_rows = (p.dyn && p.dyn_out) ? p.dyn->out_r : p.out_rows;
     extern __shared__ __align__(16) uint8_t fsm[];
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(fsm);   // [SORT_CAP]
-    // the query, widened to fp64 ONCE: the rescore is bound by F2F.F64.F32 conversions (16 per
-    // clock per SM), so converting q per row would double its cost
-    double* sq = reinterpret_cast<double*>(fsm + SORT_CAP * sizeof(unsigned long long));  // [d]
+    float* sq = reinterpret_cast<float*>(fsm + SORT_CAP * sizeof(unsigned long long));   // the query, [d] fp32
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_krem;
@@ -654,7 +653,7 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
     if (kRescore && p.g_thr) {
         // row-sharded search: every rank's bound for this query is (about to be) in my threshold
         // buffer; T = their minimum bounds the GLOBAL k-th coarse score from below (PublishBound)
-        wait_peer_flags(p.g_flags, p.g_world, XF_THR, p.g_seq, p.g_timeout_ns,
+        wait_peer_flags(p.g_flags, p.g_world, XF_THR, g_seq, p.g_timeout_ns,
                         p.gstats ? p.gstats + GS_XSTATUS : nullptr);
         float T = INFINITY;
         for (int r = 0; r < p.g_world; r++) {
@@ -673,9 +672,8 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
     if (kRescore) {
         if (threadIdx.x == 0) { s_err = 0u; s_viol = 0u; }
         for (int j = threadIdx.x; j < p.d; j += blockDim.x)
-            sq[j] = static_cast<double>(p.q32[static_cast<long long>(q) * p.d + j]);
+            sq[j] = q32[static_cast<long long>(q) * p.d + j];
         __syncthreads();
-        const double2* q2 = reinterpret_cast<const double2*>(sq);
         // Run-time certificate of the a-priori bound eps_q (prep_queries_kernel): every row that is
         // rescored anyway still carries its COARSE score in the key, so |coarse - exact| / eps_q is
         // free to check.  It is the only guard on the tensor core's fp32 accumulation behaviour.
@@ -692,33 +690,64 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
         // keys[lo..hi) <- exact (score,row) keys.  Two candidates per warp iteration: both rows'
         // loads are in flight before either reduction starts (the gather is latency-bound: 3 KB
         // from a random HBM page per row).  track_min: s_min <- smallest exact score (ordered).
+        // The gather is what this kernel is made of (1.5-3 KB from a random HBM page per row), so
+        // ALL loads of a row pair are issued before any arithmetic: `JU` float4 chunks per lane and
+        // row, fully unrolled (d <= 128 * JU; the generic loop below covers larger d).  Products
+        // are summed four at a time in fp32 (3 roundings of ~6e-8 relative on a 4-term partial)
+        // and the partials accumulated in fp64: one F2F.F64.F32 per four elements instead of one
+        // per element -- that conversion (16 / clock / SM) was the arithmetic bound of the rescore.
+        const float4* q4 = reinterpret_cast<const float4*>(sq);
+        auto dot4 = [](float4 a, float4 b) {
+            float t = a.x * b.x;
+            t = fmaf(a.y, b.y, t);
+            t = fmaf(a.z, b.z, t);
+            return fmaf(a.w, b.w, t);
+        };
         auto rescore_range = [&](int lo, int hi, bool track_min) {
+            const int d4 = p.d >> 2;
             for (int i = lo + warp; i < hi; i += 2 * nw) {
                 const int i2 = i + nw;
                 const bool has2 = i2 < hi;
-                const uint32_t row = key_row(keys[i]);
-                const uint32_t row2 = has2 ? key_row(keys[i2]) : row;
+                const unsigned long long key1 = keys[i];
+                const unsigned long long key2 = has2 ? keys[i2] : key1;
+                const uint32_t row = key_row(key1), row2 = key_row(key2);
                 double acc = 0.0, acc2 = 0.0;
-                for (int j = lane; j < p.d / 4; j += 32) {
-                    const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j, p.sh);
-                    const float4 a2 = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j, p.sh);
-                    const double2 b01 = q2[2 * j], b23 = q2[2 * j + 1];
-                    acc = fma(static_cast<double>(a.x), b01.x, acc);
-                    acc = fma(static_cast<double>(a.y), b01.y, acc);
-                    acc = fma(static_cast<double>(a.z), b23.x, acc);
-                    acc = fma(static_cast<double>(a.w), b23.y, acc);
-                    acc2 = fma(static_cast<double>(a2.x), b01.x, acc2);
-                    acc2 = fma(static_cast<double>(a2.y), b01.y, acc2);
-                    acc2 = fma(static_cast<double>(a2.z), b23.x, acc2);
-                    acc2 = fma(static_cast<double>(a2.w), b23.y, acc2);
+                if (d4 <= 32 * RESCORE_JU) {
+                    float4 a[RESCORE_JU], a2[RESCORE_JU];
+#pragma unroll
+                    for (int u = 0; u < RESCORE_JU; u++) {
+                        const int j = lane + 32 * u;
+                        a[u] = a2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j < d4) {
+                            a[u] = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j, p.sh);
+                            a2[u] = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j, p.sh);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < RESCORE_JU; u++) {
+                        const int j = lane + 32 * u;
+                        if (j < d4) {
+                            const float4 b = q4[j];
+                            acc += static_cast<double>(dot4(a[u], b));
+                            acc2 += static_cast<double>(dot4(a2[u], b));
+                        }
+                    }
+                } else {
+                    for (int j = lane; j < d4; j += 32) {
+                        const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j, p.sh);
+                        const float4 a2 = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j, p.sh);
+                        const float4 b = q4[j];
+                        acc += static_cast<double>(dot4(a, b));
+                        acc2 += static_cast<double>(dot4(a2, b));
+                    }
                 }
                 acc = warp_sum(acc);
                 acc2 = warp_sum(acc2);
                 if (lane == 0) {
                     const float s1 = static_cast<float>(acc), s2 = static_cast<float>(acc2);
                     if (cert) {
-                        certify(keys[i], s1);
-                        if (has2) certify(keys[i2], s2);
+                        certify(key1, s1);
+                        if (has2) certify(key2, s2);
                     }
                     keys[i] = make_key(s1, row);   // NaN -> high word 0
                     if (has2) keys[i2] = make_key(s2, row2);
@@ -807,8 +836,8 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const FinalizePar
         const long long o = static_cast<long long>(q) * p.k + j;
         const int owner = p.owner_per > 0 ? static_cast<int>((p.q_base + q) / p.owner_per) : -1;
         if (owner < 0 || owner == p.self_rank) {
-            p.out_scores[o] = s;
-            p.out_rows[o] = r;
+            out_scores[o] = s;
+            out_rows[o] = r;
         }
         for (int e = 0; e < p.n_extra; e++) {
             if (owner < 0 || owner == p.extra_rank[e]) {

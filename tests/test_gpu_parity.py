@@ -109,9 +109,17 @@ def test_small_batches_replay_a_cuda_graph(fo):
         assert st["fallback_queries"] == 0 and st["slabs"] >= 2 and st["coarse_launches"] == st["slabs"]
         Do, Io = fo.search(q, x, 10)
         fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
-        if st["graph_mode"] == 2:
-            assert st["coarse_ms"] > 0 and st["total_ms"] >= st["coarse_ms"]
+        assert st["total_ms"] > 0
     assert modes[0] == 1 and set(modes[1:]) == {2}, modes
+    # per-kernel times inside a graph are opt-in (event-record nodes cost ~3 us each)
+    assert e.stats()["coarse_ms"] == 0
+    e.set_option("graph_timing", 1)
+    for it in range(2):
+        e.search(q, 10)
+        st = e.stats()
+        assert st["graph_mode"] == it + 1
+    assert 0 < st["coarse_ms"] <= st["total_ms"] and st["finalize_ms"] > 0
+    e.set_option("graph_timing", 0)
     qd = torch.from_numpy(synth(48, 768, 5)).cuda()
     outs = []
     for it in range(3):                                   # device buffers: fresh output tensors per call
