@@ -273,6 +273,22 @@ cudaEvent_t get_event(std::vector<cudaEvent_t>& pool, size_t i) {
 }
 cudaEvent_t get_event(b2ip_handle h, size_t i) { return get_event(h->ev_pool, i); }
 
+// finalize_kernel<true>: [sort buffer | query fp32 | per-warp ring of `stages` rows | mbarriers]
+int rescore_ring_stages(b2ip_handle h) {
+    const size_t row_bytes = h->store16 ? static_cast<size_t>(h->d_pad) * 2 : static_cast<size_t>(h->d) * 4;
+    const size_t nw = SEL_THREADS / 32;
+    size_t ns = std::max<size_t>(2, std::min<size_t>(8, (72u << 10) / (nw * row_bytes)));
+    const size_t fixed = SORT_CAP * sizeof(unsigned long long) + ((static_cast<size_t>(h->d) * 4 + 15) & ~static_cast<size_t>(15));
+    while (ns > 1 && fixed + nw * ns * (row_bytes + 8) > (200u << 10)) ns--;
+    return static_cast<int>(ns);
+}
+size_t finalize_smem_bytes(b2ip_handle h, int stages) {
+    const size_t row_bytes = h->store16 ? static_cast<size_t>(h->d_pad) * 2 : static_cast<size_t>(h->d) * 4;
+    const size_t nw = SEL_THREADS / 32;
+    return SORT_CAP * sizeof(unsigned long long) + ((static_cast<size_t>(h->d) * 4 + 15) & ~static_cast<size_t>(15)) +
+           nw * stages * (row_bytes + 8);
+}
+
 int64_t pad_q(int64_t nq) { return (nq + 2 * TILE_Q - 1) / (2 * TILE_Q) * (2 * TILE_Q); }
 
 // ------------------------------------------------------------------------- host -> device staging
@@ -424,7 +440,7 @@ int exact_search(b2ip_handle h, const float* q32, const int* qlist_host, int64_t
     CU_TRY(h, cudaMemcpyAsync(qlist_dev, qlist_host, static_cast<size_t>(nql) * sizeof(int),
                               cudaMemcpyHostToDevice, h->stream));
     const size_t sq_bytes = static_cast<size_t>(EXACT_QB) * h->d * sizeof(float);
-    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
+    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long);     // finalize_kernel<false>: sort only
     const int sgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
     const int hgrid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(h->sm_count) * 4));
     for (int64_t g0 = 0; g0 < nql; g0 += EXACT_QB) {
@@ -532,7 +548,8 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
     RC_TRY(ensure(h, h->flags, qb * sizeof(int)));
     RC_TRY(ensure(h, h->cand, static_cast<size_t>(qb) * cap * 8));
 
-    const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(h->d) * sizeof(float);
+    const int ring_stages = rescore_ring_stages(h);
+    const size_t fin_smem = finalize_smem_bytes(h, ring_stages);
     // tensor maps of the corpus are rebuilt only when the rows moved or grew
     if (h->tmap_x_base != h->x16 || h->tmap_x_rows != n) {
         RC_TRY(make_tmap_bf16(h, &h->tmap_x_pair, h->x16, n, h->d_pad, 128));
@@ -769,6 +786,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         FinalizeParams fp{};
         fp.dyn = dyn;
         fp.dyn_out = h->ex ? 0 : 1;     // exchange: finalize writes the (stable) gather slots
+        fp.ring_stages = ring_stages;
         fp.k = k; fp.cap = cap; fp.d = h->d;
         fp.qlist = nullptr;
         fp.cand = cp.cand;
@@ -1046,7 +1064,7 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     {   // opt-in shared memory sizes, once per process and device
         // (upper bounds for the largest supported d, so handles of different d can coexist)
-        const size_t fin_smem = SORT_CAP * sizeof(unsigned long long) + static_cast<size_t>(B2IP_MAX_D) * sizeof(float);
+        const size_t fin_smem = 200u << 10;     // upper bound of finalize_smem_bytes()
         if (cudaFuncSetAttribute(coarse_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES) != cudaSuccess ||

@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 #include <float.h>
 #include "keys.cuh"
+#include "ptx_sm100.cuh"
 
 namespace b2ip {
 
@@ -595,6 +596,7 @@ struct FinalizeParams {
     unsigned int g_seq;
     long long g_timeout_ns;
     long long* gstats;
+    int ring_stages;                  // rescore: rows in flight per warp (1-D TMA ring in shared memory)
     const DynArgs* dyn;               // graph replay: q32 / g_seq (and, with dyn_out, the output buffers) come from here
     int dyn_out;
 };
@@ -670,7 +672,15 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_cons
     }
 
     if (kRescore) {
-        if (threadIdx.x == 0) { s_err = 0u; s_viol = 0u; }
+        if (threadIdx.x == 0) {
+            s_err = 0u; s_viol = 0u;
+            const int row_bytes0 = p.x32 ? p.d * 4 : p.d_pad * 2;
+            uint64_t* b0 = reinterpret_cast<uint64_t*>(
+                fsm + SORT_CAP * sizeof(unsigned long long) + ((static_cast<size_t>(p.d) * 4 + 15) & ~static_cast<size_t>(15)) +
+                static_cast<size_t>(blockDim.x >> 5) * p.ring_stages * row_bytes0);
+            for (int i = 0; i < (blockDim.x >> 5) * p.ring_stages; i++) ptx::mbar_init(&b0[i], 1);
+            ptx::fence_mbar_init();
+        }
         for (int j = threadIdx.x; j < p.d; j += blockDim.x)
             sq[j] = q32[static_cast<long long>(q) * p.d + j];
         __syncthreads();
@@ -679,84 +689,153 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_cons
         // free to check.  It is the only guard on the tensor core's fp32 accumulation behaviour.
         const float cert_eps = p.cert_eps2 ? 0.5f * p.cert_eps2[slot] : 0.f;
         const bool cert = p.gstats && cert_eps > 0.f && cert_eps <= FLT_MAX;
-        auto certify = [&](unsigned long long coarse_key, float exact) {
-            const float c = key_score(coarse_key);
-            const float e = fabsf(c - exact);
-            if (!(e <= FLT_MAX)) return;            // NaN / inf scores carry no margin (see shadow_rows_kernel)
-            const float ratio = e / cert_eps;
-            atomicMax(&s_err, __float_as_uint(ratio));
-            if (ratio > 1.0f) atomicAdd(&s_viol, 1u);
-        };
-        // keys[lo..hi) <- exact (score,row) keys.  Two candidates per warp iteration: both rows'
-        // loads are in flight before either reduction starts (the gather is latency-bound: 3 KB
-        // from a random HBM page per row).  track_min: s_min <- smallest exact score (ordered).
-        // The gather is what this kernel is made of (1.5-3 KB from a random HBM page per row), so
-        // ALL loads of a row pair are issued before any arithmetic: `JU` float4 chunks per lane and
-        // row, fully unrolled (d <= 128 * JU; the generic loop below covers larger d).  Products
-        // are summed four at a time in fp32 (3 roundings of ~6e-8 relative on a 4-term partial)
-        // and the partials accumulated in fp64: one F2F.F64.F32 per four elements instead of one
-        // per element -- that conversion (16 / clock / SM) was the arithmetic bound of the rescore.
-        const float4* q4 = reinterpret_cast<const float4*>(sq);
+        // keys[lo..hi) <- exact (score,row) keys.  track_min: s_min <- smallest exact score (ordered).
+        //
+        // The rescore is a GATHER: 1.5-3 KB from a random HBM page per surviving row, ~150 (k = 100)
+        // to ~1500 (k = 1000) rows per query.  Every row is one contiguous chunk, so it is fetched
+        // by ONE 1-D TMA (cp.async.bulk) into a per-warp ring in shared memory: the bytes in flight
+        // (ring_stages rows per warp, ~70 KB per CTA) no longer depend on registers or occupancy,
+        // and the arithmetic reads the row from shared memory against the query slice each lane
+        // keeps in registers for the whole kernel.  Products are summed four at a time in fp32 (3
+        // roundings of ~6e-8 relative on a 4-term partial) and the partials accumulated in fp64.
         auto dot4 = [](float4 a, float4 b) {
             float t = a.x * b.x;
             t = fmaf(a.y, b.y, t);
             t = fmaf(a.z, b.z, t);
             return fmaf(a.w, b.w, t);
         };
-        auto rescore_range = [&](int lo, int hi, bool track_min) {
-            const int d4 = p.d >> 2;
-            for (int i = lo + warp; i < hi; i += 2 * nw) {
-                const int i2 = i + nw;
-                const bool has2 = i2 < hi;
-                const unsigned long long key1 = keys[i];
-                const unsigned long long key2 = has2 ? keys[i2] : key1;
-                const uint32_t row = key_row(key1), row2 = key_row(key2);
-                double acc = 0.0, acc2 = 0.0;
-                if (d4 <= 32 * RESCORE_JU) {
-                    float4 a[RESCORE_JU], a2[RESCORE_JU];
+        const bool rows16 = p.x32 == nullptr;
+        const int chunk_elems = rows16 ? 8 : 4;                    // elements per 16-byte chunk of a stored row
+        const int row_bytes = rows16 ? p.d_pad * 2 : p.d * 4;
+        const int n_chunks = row_bytes >> 4;
+        const char* const row_base = rows16 ? reinterpret_cast<const char*>(p.x16)
+                                            : reinterpret_cast<const char*>(p.x32);
+        // this lane's slice of the query: chunk c = lane + 32 u covers elements [c*E, c*E + E)
+        float4 qreg[RESCORE_JU];
+        const bool q_in_regs = p.d <= 128 * RESCORE_JU;
+        if (q_in_regs) {
+#pragma unroll
+            for (int u = 0; u < RESCORE_JU; u++) {
+                // fp32 rows: float4 number (lane + 32 u); 16-bit rows: float4 numbers 2c, 2c+1 of chunk c = lane + 32 (u/2)
+                const int f4 = rows16 ? 2 * (lane + 32 * (u >> 1)) + (u & 1) : lane + 32 * u;
+                qreg[u] = (4 * f4 < p.d) ? reinterpret_cast<const float4*>(sq)[f4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        auto row_dot = [&](const uint4* srow) -> double {          // all lanes; partial of this lane
+            double acc = 0.0;
+            if (q_in_regs) {
+                if (!rows16) {
 #pragma unroll
                     for (int u = 0; u < RESCORE_JU; u++) {
-                        const int j = lane + 32 * u;
-                        a[u] = a2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (j < d4) {
-                            a[u] = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j, p.sh);
-                            a2[u] = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j, p.sh);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < RESCORE_JU; u++) {
-                        const int j = lane + 32 * u;
-                        if (j < d4) {
-                            const float4 b = q4[j];
-                            acc += static_cast<double>(dot4(a[u], b));
-                            acc2 += static_cast<double>(dot4(a2[u], b));
+                        const int c = lane + 32 * u;
+                        if (c < n_chunks) {
+                            const uint4 v = srow[c];
+                            acc += static_cast<double>(dot4(make_float4(__uint_as_float(v.x), __uint_as_float(v.y),
+                                                                        __uint_as_float(v.z), __uint_as_float(v.w)), qreg[u]));
                         }
                     }
                 } else {
-                    for (int j = lane; j < d4; j += 32) {
-                        const float4 a = load_row4(p.x32, p.x16, row, p.d, p.d_pad, j, p.sh);
-                        const float4 a2 = load_row4(p.x32, p.x16, row2, p.d, p.d_pad, j, p.sh);
-                        const float4 b = q4[j];
-                        acc += static_cast<double>(dot4(a, b));
-                        acc2 += static_cast<double>(dot4(a2, b));
+#pragma unroll
+                    for (int u = 0; u < RESCORE_JU / 2; u++) {
+                        const int c = lane + 32 * u;
+                        if (c < n_chunks) {
+                            const uint4 v = srow[c];
+                            const float2 e0 = unpack2_sh(v.x, p.sh), e1 = unpack2_sh(v.y, p.sh);
+                            const float2 e2 = unpack2_sh(v.z, p.sh), e3 = unpack2_sh(v.w, p.sh);
+                            acc += static_cast<double>(dot4(make_float4(e0.x, e0.y, e1.x, e1.y), qreg[2 * u]));
+                            acc += static_cast<double>(dot4(make_float4(e2.x, e2.y, e3.x, e3.y), qreg[2 * u + 1]));
+                        }
                     }
                 }
-                acc = warp_sum(acc);
-                acc2 = warp_sum(acc2);
-                if (lane == 0) {
-                    const float s1 = static_cast<float>(acc), s2 = static_cast<float>(acc2);
-                    if (cert) {
-                        certify(key1, s1);
-                        if (has2) certify(key2, s2);
-                    }
-                    keys[i] = make_key(s1, row);   // NaN -> high word 0
-                    if (has2) keys[i2] = make_key(s2, row2);
-                    if (track_min) {
-                        atomicMin(&s_min, order_f32(s1));                 // order(NaN) = 0: no pruning
-                        if (has2) atomicMin(&s_min, order_f32(s2));
+            } else {                                               // d > 1024: query slice from shared memory
+                const float4* q4 = reinterpret_cast<const float4*>(sq);
+                for (int c = lane; c < n_chunks; c += 32) {
+                    const uint4 v = srow[c];
+                    if (!rows16) {
+                        acc += static_cast<double>(dot4(make_float4(__uint_as_float(v.x), __uint_as_float(v.y),
+                                                                    __uint_as_float(v.z), __uint_as_float(v.w)), q4[c]));
+                    } else {
+                        const float2 e0 = unpack2_sh(v.x, p.sh), e1 = unpack2_sh(v.y, p.sh);
+                        const float2 e2 = unpack2_sh(v.z, p.sh), e3 = unpack2_sh(v.w, p.sh);
+                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 qa = (8 * c < p.d) ? q4[2 * c] : z, qb = (8 * c + 4 < p.d) ? q4[2 * c + 1] : z;
+                        acc += static_cast<double>(dot4(make_float4(e0.x, e0.y, e1.x, e1.y), qa));
+                        acc += static_cast<double>(dot4(make_float4(e2.x, e2.y, e3.x, e3.y), qb));
                     }
                 }
             }
+            return acc;
+        };
+        (void)chunk_elems;
+        const int NS = p.ring_stages;
+        uint8_t* const ring = fsm + SORT_CAP * sizeof(unsigned long long) + ((static_cast<size_t>(p.d) * 4 + 15) & ~static_cast<size_t>(15));
+        uint64_t* const bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(nw) * NS * row_bytes);
+        uint8_t* const my_ring = ring + static_cast<size_t>(warp) * NS * row_bytes;
+        uint64_t* const my_bars = bars + warp * NS;
+        // The per-row epilogue (certificate, key, minimum) is done 32 rows at a time, one row per
+        // lane, instead of by lane 0 after every row: the rescore is instruction-issue bound once
+        // the gather is asynchronous, and a serial one-lane tail was a third of its instructions.
+        const float inv_cert_eps = cert ? 1.0f / cert_eps : 0.f;
+        float w_err = 0.f;                 // lane-local maxima / minima, folded into shared memory once per warp
+        unsigned int w_viol = 0u, w_min = 0xFFFFFFFFu;
+        int st_i = 0, st_w = 0;            // ring stage of the next row to issue / to wait for
+        unsigned int ph_w = 0u;            // phase bit of stage st_w
+        auto rescore_range = [&](int lo, int hi, bool track_min) {
+            const int cnt_w = (hi - lo - warp + nw - 1) / nw;      // rows of this warp: lo + warp + n * nw
+            if (cnt_w <= 0) return;
+            auto issue = [&](int n) {                              // lane 0: fetch this warp's n-th row
+                const uint32_t row = key_row(keys[lo + warp + n * nw]);
+                ptx::mbar_expect_tx(&my_bars[st_i], static_cast<uint32_t>(row_bytes));
+                ptx::bulk_load(my_ring + static_cast<size_t>(st_i) * row_bytes,
+                               row_base + static_cast<size_t>(row) * row_bytes, static_cast<uint32_t>(row_bytes),
+                               &my_bars[st_i], ptx::kEvictFirst);
+                if (++st_i == NS) st_i = 0;
+            };
+            if (lane == 0)
+                for (int n = 0; n < min(NS, cnt_w); n++) issue(n);
+            double mine = 0.0;                                     // total of row (n0 + lane) of the current group of 32
+            auto epilogue = [&](int n0, int cnt) {                 // rows n0 .. n0+cnt-1, lane = row - n0
+                if (lane < cnt) {
+                    const int i = lo + warp + (n0 + lane) * nw;
+                    const unsigned long long key1 = keys[i];
+                    const float s1 = static_cast<float>(mine);
+                    if (cert) {
+                        const float e = fabsf(key_score(key1) - s1);
+                        if (e <= FLT_MAX) {                        // NaN / inf scores carry no margin (see shadow_rows_kernel)
+                            const float ratio = e * inv_cert_eps;
+                            w_err = fmaxf(w_err, ratio);
+                            w_viol += ratio > 1.0f ? 1u : 0u;
+                        }
+                    }
+                    keys[i] = make_key(s1, key_row(key1));         // NaN -> high word 0
+                    if (track_min) w_min = min(w_min, order_f32(s1));   // order(NaN) = 0: no pruning
+                }
+            };
+            for (int n = 0; n < cnt_w; n++) {
+                ptx::mbar_wait(&my_bars[st_w], ph_w);
+                double acc = row_dot(reinterpret_cast<const uint4*>(my_ring + static_cast<size_t>(st_w) * row_bytes));
+                if (++st_w == NS) { st_w = 0; ph_w ^= 1u; }
+                __syncwarp();                                      // every lane is done with the stage
+                if (lane == 0 && n + NS < cnt_w) issue(n + NS);
+                acc = warp_sum(acc);
+                if (lane == (n & 31)) mine = acc;
+                if ((n & 31) == 31) epilogue(n - 31, 32);
+            }
+            if (cnt_w & 31) epilogue(cnt_w & ~31, cnt_w & 31);
+        };
+        auto fold_warp_stats = [&]() {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                w_err = fmaxf(w_err, __shfl_xor_sync(0xffffffffu, w_err, o));
+                w_viol += __shfl_xor_sync(0xffffffffu, w_viol, o);
+                w_min = min(w_min, __shfl_xor_sync(0xffffffffu, w_min, o));
+            }
+            if (lane == 0) {
+                if (w_err > 0.f) atomicMax(&s_err, __float_as_uint(w_err));
+                if (w_viol) atomicAdd(&s_viol, w_viol);
+                atomicMin(&s_min, w_min);
+            }
+            w_min = 0xFFFFFFFFu;
         };
         int n_resc = n;
         if (p.eps2 && n - p.k >= 64 && n <= SORT_CAP) {   // (not worth a select for a handful of rows)
@@ -773,6 +852,7 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_cons
             const int rest = block_compact_disjoint(sbuf, n, true, 0u, pk, keys + m1, s_warp, true);
             __syncthreads();
             rescore_range(0, m1, true);
+            fold_warp_stats();
             __syncthreads();
             const uint32_t omin = s_min;
             float t2 = omin == 0u ? -INFINITY : __fsub_rd(unorder_f32(omin), 0.5f * p.eps2[slot]);
@@ -786,6 +866,7 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_cons
         } else {
             rescore_range(0, n, false);
         }
+        fold_warp_stats();
         __syncthreads();
         if (threadIdx.x == 0 && p.gstats) {
             atomicAdd(reinterpret_cast<unsigned long long*>(p.gstats + GS_RESCORED),

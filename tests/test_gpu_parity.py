@@ -523,6 +523,31 @@ def test_single_process_multi_engine_equals_one_engine(fo, tmp_path):
         assert ia == ic and np.array_equal(sa, sc)
 
 
+def test_search_knn_takes_device_queries_and_float16(fo):
+    """SURVEY 8f N4 through the drop-in: `Indexer.search_knn` given the encoder's output as a CUDA
+    tensor (float16 or float32) returns exactly what it returns for the same values as a host
+    array, chunked or not; float16 host queries equal their float32 widening (astype is exact)."""
+    import torch
+    from src.index import Indexer
+    x = synth(20_000, 768, 301, normalize=False)
+    q16 = synth(300, 768, 302, normalize=False).astype(np.float16)
+    ix = Indexer(768, 0, 8, device=0, store="f32")
+    ix.index_data([f"d{i}" for i in range(len(x))], x)
+    want = ix.search_knn(q16.astype(np.float32), 20)
+    ref = fo.OracleIndexer(768, 0, 8)
+    ref.index_data([f"d{i}" for i in range(len(x))], x)
+    for (gi, gs), (wi, ws) in zip(want[:50], ref.search_knn(q16[:50], 20)):
+        assert gi == wi and np.allclose(gs, ws, rtol=RTOL, atol=0)
+    for chunk in (16384, 64):
+        ix.knn_chunk = chunk
+        for queries in (q16, torch.from_numpy(q16).cuda(), torch.from_numpy(q16.astype(np.float32)).cuda(),
+                        torch.from_numpy(q16)):
+            got = ix.search_knn(queries, 20)
+            assert len(got) == len(want)
+            for (gi, gs), (wi, ws) in zip(got, want):
+                assert gi == wi and np.array_equal(gs, ws) and gs.dtype == np.float32
+
+
 def test_indexer_rejects_pq():
     from src.index import Indexer
     with pytest.raises(NotImplementedError):

@@ -324,6 +324,38 @@ def test_dropin_launcher_replaces_src_index_in_a_reference_style_checkout(tmp_pa
     assert "b2ip.indexer 42 ['--n_docs', '100'] b2ip.beir_search" in out.stdout and "pq rejected" in out.stdout
 
 
+def test_dropin_launcher_can_swap_a_function_the_script_defines(tmp_path, built):
+    """B2IP_DEVICE_QUERIES=1: the script's own module-level `embed_queries` is replaced AFTER the
+    script defined it and BEFORE its `if __name__ == "__main__":` block runs."""
+    import subprocess
+    import sys
+    from b2ip import dropin
+    script = tmp_path / "driver.py"
+    script.write_text(
+        "import sys\n"
+        "def embed_queries(args, queries, model, tokenizer):\n    return 'host'\n"
+        "def main():\n    print('embed ->', embed_queries(None, [], None, None), sys.argv[1:])\n"
+        "if __name__ == '__main__':\n    main()\n")
+    ns = dropin.run_script(str(script), {"embed_queries": lambda *a: "device"})
+    assert ns["embed_queries"](1, 2, 3, 4) == "device"
+    with pytest.raises(AttributeError):
+        dropin.run_script(str(script), {"no_such_function": None})
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "czech-contriever_b200"), B2IP_DEVICE_QUERIES="1")
+    # the real replacement needs torch + a model; here only that it is the one being bound
+    probe = tmp_path / "probe.py"
+    probe.write_text(
+        "def embed_queries(args, queries, model, tokenizer):\n    return 'host'\n"
+        "if __name__ == '__main__':\n    print(embed_queries.__module__, embed_queries.__name__)\n")
+    out = subprocess.run([sys.executable, "-m", "b2ip.dropin", str(probe)], capture_output=True, text=True,
+                         env=env, cwd=str(tmp_path), timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "embed_queries_device" in out.stdout
+    env["B2IP_DEVICE_QUERIES"] = "0"
+    out = subprocess.run([sys.executable, "-m", "b2ip.dropin", str(probe)], capture_output=True, text=True,
+                         env=env, cwd=str(tmp_path), timeout=120)
+    assert out.stdout.split() == ["__main__", "embed_queries"]
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/passage_retrieval.py"),
                     reason="reference checkout not present (GPU box)")
 def test_dropin_launcher_runs_the_unmodified_reference_driver(built):

@@ -1,7 +1,5 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/r2d_parity.log 2>&1; tail -5 gpurun_out/r2d_parity.log
-for cfg in "1 1" "1 0" "0 1"; do set -- $cfg; echo "== graph=$1 timing=$2"
-  B2IP_GRAPH=$1 B2IP_GRAPH_TIMING=$2 python bench.py --workload c5 --n-corpus 2625000 --steps 1000 --warmup 50 --no-cpu-baseline --no-search-knn --no-e2e > gpurun_out/r2d_c5_g$1t$2.json 2>gpurun_out/r2d_c5.err
-  python tools/show_bench.py gpurun_out/r2d_c5_g$1t$2.json | head -4; done
-for nq in 1 16; do B2IP_GRAPH=1 python bench.py --workload c5 --n-corpus 2625000 --n-queries $nq --steps 1000 --warmup 50 --no-cpu-baseline --no-search-knn --no-e2e > gpurun_out/r2d_c5_nq$nq.json 2>>gpurun_out/r2d_c5.err
-  python tools/show_bench.py gpurun_out/r2d_c5_nq$nq.json | head -3; done
-tail -5 gpurun_out/r2d_c5.err
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_random.py -m gpu -x -q > gpurun_out/r2h_parity.log 2>&1; tail -5 gpurun_out/r2h_parity.log
+python tools/regimes.py --n-corpus 2625000 --cases 100000:100,100000:1000 --reps 2 > gpurun_out/r2h_regimes_f32.log 2>&1
+python tools/regimes.py --n-corpus 2625000 --store bf16 --cases 100000:100,100000:1000 --reps 2 > gpurun_out/r2h_regimes_bf16.log 2>&1
+cat gpurun_out/r2h_regimes_f32.log gpurun_out/r2h_regimes_bf16.log | cut -c1-330
+ncu --set full --import-source on --clock-control none -k regex:finalize_kernel -c 1 -f -o gpurun_out/r2h_finalize_k1000_bf16 python tools/regimes.py --n-corpus 2625000 --store bf16 --cases 100000:1000 --reps 0 > gpurun_out/r2h_ncu1.log 2>&1; tail -1 gpurun_out/r2h_ncu1.log | cut -c1-100

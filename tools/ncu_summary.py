@@ -50,8 +50,30 @@ def full(rep, n_top=12):
         print(f"| {s:.0f} | {100 * s / tot:.1f}% | {float(r[ci['Instructions Executed']]):.0f} | `{r[ci['Source']].strip()[:70]}` | {top[1]} |")
 
 
+def lines(rep, n_top=25):
+    """Warp-stall samples per CUDA source line (needs -lineinfo): where a kernel spends its time."""
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                         capture_output=True, text=True).stdout
+    fname, out = None, []
+    for row in csv.reader(io.StringIO(src)):
+        if len(row) == 2 and row[0] == "File Path":
+            fname = row[1].split("/")[-1]
+        elif len(row) > 8 and row[2] == "-" and row[0].isdigit():      # a source-line aggregate row
+            try:
+                out.append((float(row[6] or 0), float(row[7] or 0), fname, int(row[0]), row[1].strip()))
+            except ValueError:
+                pass
+    tot = sum(o[0] for o in out) or 1.0
+    print(f"| samples | share | warp instr | line | source |\n|---:|---:|---:|---|---|")
+    for smp, ins, f, ln, text in sorted(out, key=lambda o: -o[0])[:n_top]:
+        print(f"| {smp:.0f} | {100 * smp / tot:.1f}% | {ins:.0f} | {f}:{ln} | `{text[:90]}` |")
+    print(f"| {tot:.0f} | 100% | {sum(o[1] for o in out):.0f} | total | |")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "lines":
+        lines(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 25)
     else:
         full(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 12)
