@@ -57,6 +57,28 @@ struct DevBuf {
 
 namespace { class CopyPool; }
 
+// Row storage that grows IN PLACE: a virtual address range sized for the whole device is reserved
+// once and physical chunks are mapped behind the rows as they arrive (CUDA virtual memory
+// management), so appending never needs old and new copy resident together -- a 97 GB fp32 index
+// grows chunk by chunk to exactly its final size (cudaMalloc + copy would need 1.5-2x transiently
+// and fail on the last steps).  Driver entry points are resolved at run time (no libcuda link).
+struct VmmApi {
+    CUresult (*getGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*addressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*setAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*addressFree)(CUdeviceptr, size_t) = nullptr;
+    bool ok = false;
+};
+struct VBuf {
+    CUdeviceptr base = 0;
+    size_t reserved = 0, mapped = 0;
+    std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+};
+
 struct b2ip_index_s {
     void* pin[2] = {nullptr, nullptr};    // pinned staging of host_to_device
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
@@ -66,6 +88,9 @@ struct b2ip_index_s {
     cudaStream_t stream = nullptr, own_stream = nullptr;
     float* x32 = nullptr;
     __nv_bfloat16* x16 = nullptr;
+    VmmApi vmm;                           // in-place growth of x32 / x16 (falls back to cudaMalloc + copy)
+    VBuf v32, v16;
+    size_t vmm_gran = 0;
     int64_t n = 0, cap_rows = 0, row_offset = 0;
     bool store16 = false;                 // rows ARE 16-bit (bf16 or fp16 per `sh`): no fp32 master
     int sh = SH_BF16;                     // operand type of the coarse GEMM = element type of x16
@@ -199,8 +224,106 @@ void release(DevBuf& b) {
     b.bytes = 0;
 }
 
+template <typename F>
+bool vmm_sym(const char* name, F* out) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    *out = reinterpret_cast<F>(fn);
+    return true;
+}
+
+void vmm_init(b2ip_handle h) {
+    VmmApi& a = h->vmm;
+    if (const char* e = getenv("B2IP_VMM")) if (atoi(e) == 0) return;
+    a.ok = vmm_sym("cuMemGetAllocationGranularity", &a.getGranularity) && vmm_sym("cuMemAddressReserve", &a.addressReserve) &&
+           vmm_sym("cuMemCreate", &a.create) && vmm_sym("cuMemMap", &a.map) && vmm_sym("cuMemSetAccess", &a.setAccess) &&
+           vmm_sym("cuMemUnmap", &a.unmap) && vmm_sym("cuMemRelease", &a.release) && vmm_sym("cuMemAddressFree", &a.addressFree);
+    if (!a.ok) return;
+    CUmemAllocationProp prop{};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = h->device;
+    if (a.getGranularity(&h->vmm_gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || h->vmm_gran == 0) a.ok = false;
+}
+
+// maps physical memory behind [0, bytes) of the buffer (reserving its address range on first use)
+bool vmm_grow(b2ip_handle h, VBuf& b, size_t bytes) {
+    VmmApi& a = h->vmm;
+    if (bytes <= b.mapped) return true;
+    if (!b.base) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+        b.reserved = (total_b + h->vmm_gran - 1) / h->vmm_gran * h->vmm_gran;   // a buffer never outgrows the device
+        if (a.addressReserve(&b.base, b.reserved, h->vmm_gran, 0, 0) != CUDA_SUCCESS) { b.base = 0; b.reserved = 0; return false; }
+    }
+    if (bytes > b.reserved) return false;
+    // chunks grow geometrically up to 256 MiB: a small index maps a few MiB, a large one few chunks
+    const size_t gran = h->vmm_gran;
+    const size_t max_step = std::max<size_t>(gran, 256u << 20) / gran * gran;
+    while (b.mapped < bytes) {
+        size_t step = std::max(bytes - b.mapped, b.mapped / 2);
+        step = std::min(max_step, (step + gran - 1) / gran * gran);
+        size_t len = std::min<size_t>(step, b.reserved - b.mapped);
+        CUmemAllocationProp prop{};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = h->device;
+        CUmemGenericAllocationHandle hd;
+        if (a.create(&hd, len, &prop, 0) != CUDA_SUCCESS) return false;
+        if (a.map(b.base + b.mapped, len, 0, hd, 0) != CUDA_SUCCESS) { a.release(hd); return false; }
+        CUmemAccessDesc acc{};
+        acc.location = prop.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if (a.setAccess(b.base + b.mapped, len, &acc, 1) != CUDA_SUCCESS) { a.unmap(b.base + b.mapped, len); a.release(hd); return false; }
+        b.chunks.emplace_back(hd, len);
+        b.mapped += len;
+    }
+    return true;
+}
+
+void vmm_free(b2ip_handle h, VBuf& b) {
+    if (!b.base) return;
+    size_t off = 0;
+    for (auto& c : b.chunks) { h->vmm.unmap(b.base + off, c.second); h->vmm.release(c.first); off += c.second; }
+    h->vmm.addressFree(b.base, b.reserved);
+    b = VBuf();
+}
+
 int grow_rows(b2ip_handle h, int64_t need, bool exact = false) {
     if (need <= h->cap_rows) return B2IP_OK;
+    const size_t row32 = static_cast<size_t>(h->d) * sizeof(float), row16 = static_cast<size_t>(h->d_pad) * 2;
+    if (h->vmm.ok && (h->n == 0 || h->v16.base)) {
+        // in place: the rows keep their addresses, nothing is copied
+        const bool first = h->v16.base == 0;
+        if (first && (h->x32 || h->x16)) {           // (a cudaMalloc'ed buffer from before: none when n == 0)
+            if (h->x32) cudaFree(h->x32);
+            if (h->x16) cudaFree(h->x16);
+            h->x32 = nullptr; h->x16 = nullptr; h->cap_rows = 0;
+        }
+        const bool ok = (h->store16 || vmm_grow(h, h->v32, static_cast<size_t>(need) * row32)) &&
+                        vmm_grow(h, h->v16, static_cast<size_t>(need) * row16);
+        if (ok) {
+            h->x32 = h->store16 ? nullptr : reinterpret_cast<float*>(h->v32.base);
+            h->x16 = reinterpret_cast<__nv_bfloat16*>(h->v16.base);
+            int64_t cap = static_cast<int64_t>(h->v16.mapped / row16);
+            if (!h->store16) cap = std::min<int64_t>(cap, static_cast<int64_t>(h->v32.mapped / row32));
+            h->cap_rows = cap;
+            if (first) h->ws_gen++;
+            return B2IP_OK;
+        }
+        if (h->n > 0 || !first)
+            return fail(h, B2IP_ERR_OOM, "growing the index to %lld rows failed (device memory exhausted)",
+                        static_cast<long long>(need));
+        // nothing stored yet and the very first mapping failed: use plain allocations instead
+        vmm_free(h, h->v32);
+        vmm_free(h, h->v16);
+        h->x32 = nullptr; h->x16 = nullptr; h->cap_rows = 0;
+        h->vmm.ok = false;
+    }
     int64_t ncap = need;
     if (!exact) ncap = std::max<int64_t>(std::max<int64_t>(need, h->cap_rows + h->cap_rows / 2), 4096);
     float* nx32 = nullptr;
@@ -275,18 +398,18 @@ cudaEvent_t get_event(b2ip_handle h, size_t i) { return get_event(h->ev_pool, i)
 
 // finalize_kernel<true>: [sort buffer | query fp32 | per-warp ring of `stages` rows | mbarriers]
 int rescore_ring_stages(b2ip_handle h) {
+    // ~64 KB of rows in flight per CTA (8 warps x stages x row): three CTAs per SM
     const size_t row_bytes = h->store16 ? static_cast<size_t>(h->d_pad) * 2 : static_cast<size_t>(h->d) * 4;
     const size_t nw = SEL_THREADS / 32;
-    size_t ns = std::max<size_t>(2, std::min<size_t>(8, (72u << 10) / (nw * row_bytes)));
-    const size_t fixed = SORT_CAP * sizeof(unsigned long long) + ((static_cast<size_t>(h->d) * 4 + 15) & ~static_cast<size_t>(15));
-    while (ns > 1 && fixed + nw * ns * (row_bytes + 8) > (200u << 10)) ns--;
+    size_t ns = std::max<size_t>(2, std::min<size_t>(8, (64u << 10) / (nw * row_bytes)));
+    while (ns > 1 && nw * ns * (row_bytes + 8) + static_cast<size_t>(h->d) * 4 + 64 > (200u << 10)) ns--;
     return static_cast<int>(ns);
 }
 size_t finalize_smem_bytes(b2ip_handle h, int stages) {
     const size_t row_bytes = h->store16 ? static_cast<size_t>(h->d_pad) * 2 : static_cast<size_t>(h->d) * 4;
     const size_t nw = SEL_THREADS / 32;
-    return SORT_CAP * sizeof(unsigned long long) + ((static_cast<size_t>(h->d) * 4 + 15) & ~static_cast<size_t>(15)) +
-           nw * stages * (row_bytes + 8);
+    const size_t uni = std::max<size_t>(SORT_CAP * sizeof(unsigned long long), nw * stages * row_bytes);
+    return uni + ((static_cast<size_t>(h->d) * 4 + 15) & ~static_cast<size_t>(15)) + nw * stages * 8;
 }
 
 int64_t pad_q(int64_t nq) { return (nq + 2 * TILE_Q - 1) / (2 * TILE_Q) * (2 * TILE_Q); }
@@ -1043,6 +1166,7 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     };
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(B2IP_ERR_CUDA, "cudaStreamCreate");
+    vmm_init(h);
     h->stream = h->own_stream;
     if (cudaMalloc(&h->norm_stats, 2 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&h->gstats, GS_COUNT * sizeof(long long)) != cudaSuccess ||
@@ -1098,8 +1222,13 @@ void b2ip_destroy(b2ip_handle h) {
                       &h->out_s, &h->out_r, &h->exact_scores, &h->exact_misc, &h->qlist, &h->stage,
                       &h->seg_tab})
         release(*b);
-    if (h->x32) cudaFree(h->x32);
-    if (h->x16) cudaFree(h->x16);
+    if (h->v16.base || h->v32.base) {
+        vmm_free(h, h->v32);
+        vmm_free(h, h->v16);
+    } else {
+        if (h->x32) cudaFree(h->x32);
+        if (h->x16) cudaFree(h->x16);
+    }
     if (h->norm_stats) cudaFree(h->norm_stats);
     if (h->gstats) cudaFree(h->gstats);
     if (h->h_gstats) cudaFreeHost(h->h_gstats);

@@ -617,7 +617,7 @@ __device__ void block_bitonic_desc(unsigned long long* s, int P) {
 }
 
 template <bool kRescore>
-__global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_constant__ FinalizeParams p) {
+__global__ void __launch_bounds__(SEL_THREADS, 3) finalize_kernel(const __grid_constant__ FinalizeParams p) {
     // graph replay: the per-call values come from DynArgs (the parameter block itself stays in
     // constant memory: no local copy)
     const float* const q32 = p.dyn ? p.dyn->q32 : p.q32;
@@ -626,7 +626,13 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_cons
     long long* const out_rows = (p.dyn && p.dyn_out) ? p.dyn->out_r : p.out_rows;
     extern __shared__ __align__(16) uint8_t fsm[];
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(fsm);   // [SORT_CAP]
-    float* sq = reinterpret_cast<float*>(fsm + SORT_CAP * sizeof(unsigned long long));   // the query, [d] fp32
+    // dynamic shared memory: [sort buffer, aliased by the rescore's row ring | query fp32 [d] | ring mbarriers]
+    // (the ring is live only inside rescore_range, the sort buffer only outside of it)
+    const size_t union_bytes = kRescore ? max(static_cast<size_t>(SORT_CAP) * sizeof(unsigned long long),
+                                              static_cast<size_t>(blockDim.x >> 5) * p.ring_stages *
+                                                  (p.x32 ? static_cast<size_t>(p.d) * 4 : static_cast<size_t>(p.d_pad) * 2))
+                                        : static_cast<size_t>(SORT_CAP) * sizeof(unsigned long long);
+    float* sq = reinterpret_cast<float*>(fsm + union_bytes);                             // the query, [d] fp32
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_krem;
@@ -674,10 +680,7 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_cons
     if (kRescore) {
         if (threadIdx.x == 0) {
             s_err = 0u; s_viol = 0u;
-            const int row_bytes0 = p.x32 ? p.d * 4 : p.d_pad * 2;
-            uint64_t* b0 = reinterpret_cast<uint64_t*>(
-                fsm + SORT_CAP * sizeof(unsigned long long) + ((static_cast<size_t>(p.d) * 4 + 15) & ~static_cast<size_t>(15)) +
-                static_cast<size_t>(blockDim.x >> 5) * p.ring_stages * row_bytes0);
+            uint64_t* b0 = reinterpret_cast<uint64_t*>(fsm + union_bytes + ((static_cast<size_t>(p.d) * 4 + 15) & ~static_cast<size_t>(15)));
             for (int i = 0; i < (blockDim.x >> 5) * p.ring_stages; i++) ptx::mbar_init(&b0[i], 1);
             ptx::fence_mbar_init();
         }
@@ -768,8 +771,8 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_cons
         };
         (void)chunk_elems;
         const int NS = p.ring_stages;
-        uint8_t* const ring = fsm + SORT_CAP * sizeof(unsigned long long) + ((static_cast<size_t>(p.d) * 4 + 15) & ~static_cast<size_t>(15));
-        uint64_t* const bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(nw) * NS * row_bytes);
+        uint8_t* const ring = fsm;                                 // aliases the sort buffer (see the layout note above)
+        uint64_t* const bars = reinterpret_cast<uint64_t*>(fsm + union_bytes + ((static_cast<size_t>(p.d) * 4 + 15) & ~static_cast<size_t>(15)));
         uint8_t* const my_ring = ring + static_cast<size_t>(warp) * NS * row_bytes;
         uint64_t* const my_bars = bars + warp * NS;
         // The per-row epilogue (certificate, key, minimum) is done 32 rows at a time, one row per
@@ -850,6 +853,7 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_cons
             const unsigned long long pk = block_radix_select(sbuf, n, p.k, 4, hist, &s_prefix, &s_krem);
             const int m1 = block_compact_disjoint(sbuf, n, true, 0u, pk, keys, s_warp);            // T
             const int rest = block_compact_disjoint(sbuf, n, true, 0u, pk, keys + m1, s_warp, true);
+            ptx::fence_proxy_async_smem();               // sbuf (generic proxy) is about to be overwritten by TMA
             __syncthreads();
             rescore_range(0, m1, true);
             fold_warp_stats();
@@ -860,10 +864,13 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const __grid_cons
             t2 = nextafterf(t2, -INFINITY);                  // kept: coarse > t2
             const int m2 = block_compact_disjoint(keys + m1, rest, false, order_f32(t2), 0ull, sbuf, s_warp);
             for (int i = threadIdx.x; i < m2; i += blockDim.x) keys[m1 + i] = sbuf[i];
+            ptx::fence_proxy_async_smem();
             __syncthreads();
             rescore_range(m1, m1 + m2, false);
             n_resc = m1 + m2;
         } else {
+            ptx::fence_proxy_async_smem();               // (the fused refresh staged the list in sbuf)
+            __syncthreads();
             rescore_range(0, n, false);
         }
         fold_warp_stats();

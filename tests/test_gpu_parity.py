@@ -13,6 +13,7 @@ import pytest
 from helpers import ingest_like_reference_driver, synth
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 RTOL = 1e-5
 
@@ -400,6 +401,42 @@ def test_incremental_adds_equal_one_add(fo):
     D, I = e.search(q, 100)
     Do, Io = fo.search(q, x, 100)
     fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+
+
+def test_rows_grow_in_place_and_match_the_copying_fallback(fo):
+    """The index grows in place (CUDA virtual memory management: no reserve, no regrowth copy) --
+    many small and large appends give the same rows and answers as one add, and as the
+    cudaMalloc + copy fallback (B2IP_VMM=0) run in a fresh process."""
+    import subprocess
+    import sys
+    from b2ip import Engine
+    x = synth(70_000, 256, 41)
+    q = synth(33, 256, 42)
+    one = Engine(256, 0)
+    one.add(x)
+    many = Engine(256, 0)
+    cuts = [0, 1, 2, 300, 301, 5000, 5001, 40_000, 70_000]
+    for a, b in zip(cuts, cuts[1:]):
+        many.add(x[a:b])
+    assert many.ntotal == 70_000
+    np.testing.assert_array_equal(many.export_rows(0, 70_000), x)
+    Da, Ia = one.search(q, 50)
+    Db, Ib = many.search(q, 50)
+    assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db)
+    code = (
+        "import sys, numpy as np; sys.path[:0] = %r\n"
+        "from helpers import synth; from b2ip import Engine\n"
+        "x = synth(70_000, 256, 41); q = synth(33, 256, 42); e = Engine(256, 0)\n"
+        "[e.add(x[a:b]) for a, b in zip(%r, %r)]\n"
+        "D, I = e.search(q, 50); np.save(sys.argv[1], I); np.save(sys.argv[2], D)\n"
+    ) % ([os.path.join(ROOT, "czech-contriever_b200"), os.path.join(ROOT, "tests"), ROOT], cuts[:-1], cuts[1:])
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        fi, fd = os.path.join(td, "I.npy"), os.path.join(td, "D.npy")
+        out = subprocess.run([sys.executable, "-c", code, fi, fd], env=dict(os.environ, B2IP_VMM="0"),
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert np.array_equal(np.load(fi), Ia) and np.array_equal(np.load(fd), Da)
 
 
 def test_torch_device_buffers(fo):
