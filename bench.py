@@ -701,7 +701,8 @@ def main():
 
     def run_secondary(name, ix, rows_local, nq2, k2, bound, steps2, warm2, n_rows):
         q2 = q_dev[:nq2].contiguous()
-        ms2, agg2, res2, _ = timed_device_steps(torch, D, ix, q2, k2, steps2, warm2, world, light=(bound == "hbm"))
+        ms2, agg2, res2, clocks2 = timed_device_steps(torch, D, ix, q2, k2, steps2, warm2, world,
+                                                      sample_clocks_on=local_rank, light=(bound == "hbm"))
         a, b = shard_bounds(n_rows, world, rank)
         pr = parity_probe(torch, dist, D, res2, q2, k2, d, a, b, world, rank, dev,
                           lambda x, y: _probe_rows(x, y, ix))
@@ -710,7 +711,8 @@ def main():
             "ms_per_step": ms2, "steps": steps2, "warmup": warm2, "n_queries": nq2, "k": k2,
             "store": ix.engine.store, "rows_per_gpu": rows_local,
             "roofline": roofline_of(args, D, agg2, steps2, ms2, rows_local, nq2, bound, d),
-            "parity_probe": pr,
+            "parity_probe": pr, "clocks": clocks2,
+            "graph_replay": bool(ix.engine.stats().get("graph_mode", 0) == 2),
             "rescored_per_query": agg2["rescored"] / steps2 / nq2,
             "fallback_queries": int(agg2["fallback"]),
             "rank0_ms_per_step": {"coarse": agg2["coarse_ms"] / steps2, "refresh": agg2["refresh_ms"] / steps2,

@@ -1371,8 +1371,15 @@ int b2ip_add(b2ip_handle h, int64_t n, const void* rows, int src_dtype, int mem)
 int64_t b2ip_ntotal(b2ip_handle h) { return h ? h->n : -1; }
 int b2ip_dim(b2ip_handle h) { return h ? h->d : -1; }
 
+// Global row ids travel through the merge kernels as 32-bit key halves (keys.cuh): a sharded
+// index may hold at most 2^32 - 1 rows in total.  Checked where ids are assigned and at search time.
+constexpr int64_t MAX_GLOBAL_ROWS = 0xFFFFFFFFll;
+
 int b2ip_set_row_offset(b2ip_handle h, int64_t offset) {
     if (!h || offset < 0) return B2IP_ERR_INVALID;
+    if (offset + h->n > MAX_GLOBAL_ROWS)
+        return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_set_row_offset: offset %lld + %lld rows exceeds the 2^32 - 1 global row ids "
+                    "the merge supports", (long long)offset, (long long)h->n);
     h->opt_gen++;
     h->row_offset = offset;
     return B2IP_OK;
@@ -1386,6 +1393,12 @@ int b2ip_set_row_segments(b2ip_handle h, int n_segments, const int64_t* local_st
         if (local_start[i] < 0 || global_start[i] < 0 || (i == 0 && local_start[0] != 0) ||
             (i > 0 && (local_start[i] <= local_start[i - 1] || global_start[i] <= global_start[i - 1])))
             return fail(h, B2IP_ERR_INVALID, "b2ip_set_row_segments: segment %d out of order", i);
+    }
+    if (n_segments > 0) {
+        // the last segment reaches the highest id: global_start + (rows held - its local start)
+        const int64_t top = global_start[n_segments - 1] + std::max<int64_t>(h->n - local_start[n_segments - 1], 0);
+        if (top > MAX_GLOBAL_ROWS)
+            return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_set_row_segments: global row ids up to %lld exceed 2^32 - 1", (long long)top);
     }
     Guard g(h->device);
     if (n_segments > 0) {
@@ -1423,6 +1436,9 @@ int b2ip_search_ex(b2ip_handle h, int64_t nq, const void* queries_any, int q_dty
     if (mode < B2IP_MODE_AUTO || mode > B2IP_MODE_EXACT) return fail(h, B2IP_ERR_INVALID, "b2ip_search: mode=%d", mode);
     if (mem != B2IP_MEM_HOST && mem != B2IP_MEM_DEVICE) return fail(h, B2IP_ERR_INVALID, "b2ip_search: mem=%d", mem);
     if (nq >= (1ll << 31)) return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_search: nq too large");
+    if (h->n_seg == 0 && h->row_offset + h->n > MAX_GLOBAL_ROWS)
+        return fail(h, B2IP_ERR_UNSUPPORTED, "b2ip_search: row offset %lld + %lld rows exceeds 2^32 - 1 global row ids",
+                    (long long)h->row_offset, (long long)h->n);
     Guard g(h->device);
     if (nq == 0) { memset(&h->stats, 0, sizeof(h->stats)); h->timing_pending = false; return B2IP_OK; }
     const size_t q_count = static_cast<size_t>(nq) * h->d;

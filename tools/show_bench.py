@@ -15,4 +15,4 @@ if l.get("cpu_baseline"):
     print("  cpu", c.get("value"), c.get("cores"), c.get("seconds_per_step"), [(e["batch"], round(e["ms_per_batch"])) for e in c.get("extra_legs", [])])
 for k, v in (l.get("secondary") or {}).items():
     r = v["roofline"]
-    print(f"  {k}: {v['value']:.1f} QPS  {v['ms_per_step']:.4f} ms  roof {r['achieved']:.1f} {r['unit']} frac {r['frac']:.3f} whole {r.get('whole_batch_frac_16bit')}  probe {v['parity_probe']['pass']} resc/q {v['rescored_per_query']:.1f} {v['rank0_ms_per_step']}")
+    print(f"  {k}: {v['value']:.1f} QPS  {v['ms_per_step']:.4f} ms  roof {r['achieved']:.1f} {r['unit']} frac {r['frac']:.3f} whole {r.get('whole_batch_frac_16bit')}  probe {v['parity_probe']['pass']} clk {(v.get('clocks') or {}).get('sm_mhz')} graph {v.get('graph_replay')} resc/q {v['rescored_per_query']:.1f} {v['rank0_ms_per_step']}")
