@@ -600,8 +600,12 @@ def main():
         raise SystemExit("bench.py --impl b2ip needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # a host-only group for the phase where rank 0 alone drives every GPU: an NCCL barrier
+        # would leave a spinning kernel on the waiting ranks' GPUs and take SMs from the measurement
+        cpu_group = dist.new_group(backend="gloo")
     D = Dist(torch, dist, world, dev)
 
     N, nq, k, d = args.n_corpus, args.n_queries, args.k, args.d
@@ -812,6 +816,7 @@ def main():
             del index
             torch.cuda.empty_cache()
             D.barrier()
+            torch.cuda.synchronize()
             if rank == 0:
                 ixr = Indexer(d, 0, 8, device=list(range(world)), store="f32")
                 ixr.index.reserve(N)
@@ -828,7 +833,7 @@ def main():
                        "call": "Indexer(device='all').search_knn: one process, MultiGpuEngine over all GPUs "
                                "(B2IP_DEVICES=all for an unmodified passage_retrieval.py)"}
                 ixr.index.close()
-            D.barrier()
+            dist.barrier(group=cpu_group)       # host-side wait: the other ranks' GPUs stay idle meanwhile
 
     if rank == 0:
         line = {

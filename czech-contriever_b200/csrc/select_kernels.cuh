@@ -310,12 +310,17 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
 // ---------------------------------------------------------------------------------------
 // Top `n_bytes` bytes of the k-th largest of keys[0..n) (1 <= k <= n); low bytes are zero.
 // With n_bytes = 4 that is the k-th largest SCORE, with 8 the k-th largest key.
+// A threshold only needs a LOWER BOUND of the k-th score: n_bytes = 3 fixes sign, exponent and 15
+// mantissa bits (the bound is at most 2^-15 relative below the true value, ~1/500 of the error
+// margin it is combined with) and saves a pass.  first_pass / prefix0: leading bytes all keys are
+// known to share (see common_prefix_bytes) are not counted again.
 __device__ unsigned long long block_radix_select(const unsigned long long* __restrict__ keys,
                                                  int n, int k, int n_bytes, unsigned int* hist,
-                                                 unsigned long long* s_prefix, int* s_krem) {
-    unsigned long long prefix = 0;
+                                                 unsigned long long* s_prefix, int* s_krem,
+                                                 int first_pass = 0, unsigned long long prefix0 = 0ull) {
+    unsigned long long prefix = prefix0;
     int krem = k;
-    for (int pass = 0; pass < n_bytes; pass++) {
+    for (int pass = first_pass; pass < n_bytes; pass++) {
         const int shift = 56 - 8 * pass;
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
@@ -463,6 +468,7 @@ __device__ int refresh_list(int q, int k, int cap, unsigned long long* __restric
                             int* s_warp) {
     const int n = cnt[q];
     const int prev = kept[q];
+    if (threadIdx.x == 0) { s_warp[0] = -1; s_warp[1] = 0; }   // AND / OR of the staged keys' high words
     __syncthreads();                                 // everyone has read the counters
     if (n > cap) {
         // more hits than the list holds: this query is re-run on the exact path
@@ -485,12 +491,34 @@ __device__ int refresh_list(int q, int k, int cap, unsigned long long* __restric
     }
     unsigned long long* keys = cand + static_cast<long long>(q) * cap;
     const unsigned long long* src = keys;
+    int first_pass = 0;
+    unsigned long long prefix0 = 0ull;
     if (n <= REFRESH_SMEM_KEYS) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) scratch[i] = keys[i];
+        // the scores of one list lie in a narrow range: the leading byte(s) they all share are
+        // found while the list is staged (AND / OR of the high words) and skipped by the select
+        unsigned int a = 0xFFFFFFFFu, o = 0u;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long key = keys[i];
+            scratch[i] = key;
+            a &= static_cast<unsigned int>(key >> 32);
+            o |= static_cast<unsigned int>(key >> 32);
+        }
+        a = __reduce_and_sync(0xffffffffu, a);
+        o = __reduce_or_sync(0xffffffffu, o);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAnd(reinterpret_cast<unsigned int*>(&s_warp[0]), a);
+            atomicOr(reinterpret_cast<unsigned int*>(&s_warp[1]), o);
+        }
         __syncthreads();
         src = scratch;
+        const unsigned int ah = static_cast<unsigned int>(s_warp[0]), oh = static_cast<unsigned int>(s_warp[1]);
+        const int common = (ah == oh) ? 32 : __clz(static_cast<int>(ah ^ oh));
+        first_pass = min(common >> 3, 3);
+        if (first_pass > 0)
+            prefix0 = static_cast<unsigned long long>(ah & (0xFFFFFFFFu << (32 - 8 * first_pass))) << 32;
+        __syncthreads();                             // s_warp is reused by the compaction below
     }
-    const unsigned long long pk = block_radix_select(src, n, k, 4, hist, s_prefix, s_krem);
+    const unsigned long long pk = block_radix_select(src, n, k, 3, hist, s_prefix, s_krem, first_pass, prefix0);
     const float ck = unorder_f32(static_cast<uint32_t>(pk >> 32));
     float t = __fsub_rd(ck, eps2[q]);
     if (!(t == t)) t = -INFINITY;                    // inf - inf: no usable threshold
@@ -539,7 +567,7 @@ refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
         if (n >= pub.m_rank) {
             __syncthreads();                         // the compacted list is visible to every warp
             const unsigned long long pk = block_radix_select(cand + static_cast<long long>(q) * cap, n,
-                                                             pub.m_rank, 4, hist, &s_prefix, &s_krem);
+                                                             pub.m_rank, 3, hist, &s_prefix, &s_krem);
             if ((pk >> 32) != 0ull) bound = unorder_f32(static_cast<uint32_t>(pk >> 32));   // 0 = a NaN score
         }
         if (threadIdx.x < pub.n_dst) pub.dst[threadIdx.x][q] = bound;
@@ -850,7 +878,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) finalize_kernel(const __grid_c
             for (int i = threadIdx.x; i < n; i += blockDim.x) sbuf[i] = keys[i];
             if (threadIdx.x == 0) s_min = 0xFFFFFFFFu;
             __syncthreads();
-            const unsigned long long pk = block_radix_select(sbuf, n, p.k, 4, hist, &s_prefix, &s_krem);
+            // (3 bytes: T is then a superset of the k best coarse scores -- at least k rows, as needed)
+            const unsigned long long pk = block_radix_select(sbuf, n, p.k, 3, hist, &s_prefix, &s_krem);
             const int m1 = block_compact_disjoint(sbuf, n, true, 0u, pk, keys, s_warp);            // T
             const int rest = block_compact_disjoint(sbuf, n, true, 0u, pk, keys + m1, s_warp, true);
             ptx::fence_proxy_async_smem();               // sbuf (generic proxy) is about to be overwritten by TMA
