@@ -685,7 +685,9 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
 
     // global threshold round of the peer-direct exchange: one query batch only (the flag carries
     // one sequence number per search); every rank takes the same decision (same nq, k, budget)
-    const bool thr_round = h->ex && h->ex->gthr[0] && nq <= qb && h->ex->thr_stride >= nq;
+    // -- and not in the latency regime (nq <= 2048): there the extra flag round (one more launch,
+    // one more cross-rank wait) costs more than rescoring a few dozen rows per query less
+    const bool thr_round = h->ex && h->ex->gthr[0] && nq <= qb && h->ex->thr_stride >= nq && nq > 2048;
     h->ex_thr = thr_round;
     const bool fuse_refresh = h->fuse_refresh && !thr_round;
     size_t ev_used = 0;

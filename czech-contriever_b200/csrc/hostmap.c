@@ -5,25 +5,151 @@
  * Replaces the reference's nq*k-iteration Python comprehension
  *     db_ids = [[str(self.index_id_to_db_id[i]) for i in query_top_idxs] for query_top_idxs in indexes]
  *     result.extend([(db_ids[i], scores[i]) for i in range(len(db_ids))])
- * (reference src/index.py:44-45) with one C loop that produces the SAME objects: a list of
+ * (reference src/index.py:44-45) with C that produces the SAME objects: a list of
  * (list[str] of length k, scores_row) tuples.  `str(x)` of an exact `str` is x itself, which is
  * what the reference's ids are (TSV ids, src/data.py:668-672), so the common case is a pointer
  * copy + incref; any other id type goes through PyObject_Str exactly like the reference.
  * Negative rows index from the end like a Python list does (the reference's `[-1]` quirk for
  * faiss's -1 padding when the index holds fewer than k rows); out-of-range rows raise IndexError.
  *
- * The loop is a random gather over a 21M-entry pointer array and 21M object headers (two cache
- * misses per id): both are software-prefetched a few ids ahead, which is worth ~5x over numpy's
- * fancy-index + tolist (measured in tools/hostmap_bench.py).
+ * The work is a random gather over a 21M-entry pointer array and 21M object headers: two cache
+ * misses per id, ~50 ns per id on one core even with software prefetch -- 0.5 s for 100k x 100
+ * results, more than an 8-GPU search takes.  So the gather runs on a small pool of helper threads:
+ *   - the calling thread (which holds the GIL for the whole call, so no Python code runs anywhere
+ *     else in the process) first creates every result list / tuple;
+ *   - then it and the helpers fill disjoint ranges of result rows: item pointer into the list
+ *     slot, reference count raised with an ATOMIC add (several threads may hit the same id);
+ *     immortal objects are left alone like Py_INCREF does; an id that is not an exact `str` is
+ *     left for the calling thread, which calls PyObject_Str on it afterwards (object creation
+ *     needs the GIL holder);
+ *   - the helpers never allocate, never call into the interpreter and touch nothing but
+ *     `ob_refcnt` of the id objects and slots of lists nobody else can see yet.
+ * B2IP_MAP_THREADS sets the number of threads (default: min(8, online cores); 1 = serial).
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
+#include <pthread.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <unistd.h>
 
-#define PF_FAR 24   /* ids ahead for the ob_item[] slot */
-#define PF_NEAR 8   /* ids ahead for the object header (its refcount is written) */
+#define PF_FAR 32   /* ids ahead for the ob_item[] slot */
+#define PF_NEAR 12  /* ids ahead for the object header (its refcount is written) */
+#define MAX_THREADS 16
+#define PAR_MIN_IDS 32768   /* below this the pool's wake-up costs more than it saves */
 
 static inline Py_ssize_t norm_row(int64_t r, Py_ssize_t n) { return (Py_ssize_t)(r < 0 ? r + n : r); }
+
+typedef struct {
+    PyObject** items;        /* ids->ob_item */
+    Py_ssize_t n;            /* len(ids) */
+    const int64_t* rows;     /* [nq*k] */
+    PyObject** row_lists;    /* [nq] result row lists (items NULL on entry) */
+    Py_ssize_t nq, k;
+    int bad;                 /* a row index was out of range */
+    int leftover;            /* some id is not an exact str: slot left NULL for the caller */
+} job_t;
+
+/* rows [q0, q1): item pointers + atomic increfs.  No interpreter calls. */
+static void fill_range(job_t* jb, Py_ssize_t q0, Py_ssize_t q1) {
+    PyObject** items = jb->items;
+    const Py_ssize_t n = jb->n, k = jb->k;
+    const int64_t* r = jb->rows;
+    const Py_ssize_t t_end = q1 * k;
+    int bad = 0, leftover = 0;
+    for (Py_ssize_t q = q0; q < q1 && !bad; q++) {
+        PyObject** dst = ((PyListObject*)jb->row_lists[q])->ob_item;
+        const Py_ssize_t base = q * k;
+        for (Py_ssize_t j = 0; j < k; j++) {
+            const Py_ssize_t t = base + j;
+            if (t + PF_FAR < t_end) {
+                const Py_ssize_t f = norm_row(r[t + PF_FAR], n);
+                if ((size_t)f < (size_t)n) __builtin_prefetch(items + f, 0, 0);
+            }
+            if (t + PF_NEAR < t_end) {
+                const Py_ssize_t f = norm_row(r[t + PF_NEAR], n);
+                if ((size_t)f < (size_t)n) __builtin_prefetch(items[f], 1, 0);
+            }
+            const Py_ssize_t i = norm_row(r[t], n);
+            if ((size_t)i >= (size_t)n) { bad = 1; break; }
+            PyObject* item = items[i];
+            if (PyUnicode_CheckExact(item)) {
+                if (!_Py_IsImmortal(item)) __atomic_fetch_add(&item->ob_refcnt, 1, __ATOMIC_RELAXED);
+                dst[j] = item;
+            } else {
+                leftover = 1;            /* dst[j] stays NULL: str(item) by the GIL holder */
+            }
+        }
+    }
+    if (bad) __atomic_store_n(&jb->bad, 1, __ATOMIC_RELAXED);
+    if (leftover) __atomic_store_n(&jb->leftover, 1, __ATOMIC_RELAXED);
+}
+
+/* ---------------------------------------------------------------- helper pool */
+static struct {
+    pthread_t th[MAX_THREADS];
+    int n_helpers;           /* threads besides the caller */
+    int started;
+    pthread_mutex_t m;
+    pthread_cond_t wake, done;
+    unsigned long gen;
+    int left;
+    job_t* job;
+    Py_ssize_t per;          /* rows per participant */
+} pool = {.m = PTHREAD_MUTEX_INITIALIZER, .wake = PTHREAD_COND_INITIALIZER, .done = PTHREAD_COND_INITIALIZER};
+
+static void* helper_main(void* arg) {
+    const int me = (int)(intptr_t)arg;       /* participant index 1..n_helpers (0 = the caller) */
+    unsigned long seen = 0;
+    pthread_mutex_lock(&pool.m);
+    for (;;) {
+        while (pool.gen == seen) pthread_cond_wait(&pool.wake, &pool.m);
+        seen = pool.gen;
+        job_t* jb = pool.job;
+        const Py_ssize_t per = pool.per;
+        pthread_mutex_unlock(&pool.m);
+        Py_ssize_t q0 = me * per, q1 = q0 + per;
+        if (q0 > jb->nq) q0 = jb->nq;
+        if (q1 > jb->nq) q1 = jb->nq;
+        if (q1 > q0) fill_range(jb, q0, q1);
+        pthread_mutex_lock(&pool.m);
+        if (--pool.left == 0) pthread_cond_signal(&pool.done);
+    }
+    return NULL;
+}
+
+static int pool_threads(void) {
+    if (!pool.started) {
+        pool.started = 1;
+        long want = sysconf(_SC_NPROCESSORS_ONLN);
+        if (want > 8) want = 8;
+        const char* e = getenv("B2IP_MAP_THREADS");
+        if (e) want = atol(e);
+        if (want < 1) want = 1;
+        if (want > MAX_THREADS) want = MAX_THREADS;
+        pool.n_helpers = 0;
+        for (long i = 1; i < want; i++) {
+            if (pthread_create(&pool.th[pool.n_helpers], NULL, helper_main, (void*)(intptr_t)(pool.n_helpers + 1)) != 0) break;
+            pthread_detach(pool.th[pool.n_helpers]);
+            pool.n_helpers++;
+        }
+    }
+    return pool.n_helpers + 1;
+}
+
+static void run_job(job_t* jb) {
+    const int T = (jb->nq * jb->k >= PAR_MIN_IDS) ? pool_threads() : 1;
+    if (T <= 1) { fill_range(jb, 0, jb->nq); return; }
+    const Py_ssize_t per = (jb->nq + T - 1) / T;
+    pthread_mutex_lock(&pool.m);
+    pool.job = jb; pool.per = per; pool.left = pool.n_helpers; pool.gen++;
+    pthread_cond_broadcast(&pool.wake);
+    pthread_mutex_unlock(&pool.m);
+    fill_range(jb, 0, per < jb->nq ? per : jb->nq);          /* the caller is participant 0 */
+    pthread_mutex_lock(&pool.m);
+    while (pool.left != 0) pthread_cond_wait(&pool.done, &pool.m);
+    pthread_mutex_unlock(&pool.m);
+}
 
 /* map_ids(ids: list, rows: int64 C-contiguous buffer [nq*k], nq: int, k: int, scores: sequence | None)
  *   -> [ (list[str], scores[i]) ... ]   (or [list[str] ...] when scores is None) */
@@ -35,6 +161,7 @@ static PyObject* map_ids(PyObject* self, PyObject* args) {
     if (!PyArg_ParseTuple(args, "O!y*nnO", &PyList_Type, &ids, &rows, &nq, &k, &scores)) return NULL;
     PyObject* out = NULL;
     PyObject* fast_scores = NULL;
+    PyObject** row_lists = NULL;
     if (nq < 0 || k < 0 || rows.len != (Py_ssize_t)(nq * k * (Py_ssize_t)sizeof(int64_t))) {
         PyErr_SetString(PyExc_ValueError, "map_ids: rows buffer is not int64[nq*k]");
         goto fail;
@@ -47,15 +174,14 @@ static PyObject* map_ids(PyObject* self, PyObject* args) {
             goto fail;
         }
     }
-    const int64_t* r = (const int64_t*)rows.buf;
-    const Py_ssize_t n = PyList_GET_SIZE(ids);
-    const Py_ssize_t total = nq * k;
     out = PyList_New(nq);
     if (!out) goto fail;
+    row_lists = (PyObject**)malloc((size_t)(nq > 0 ? nq : 1) * sizeof(PyObject*));
+    if (!row_lists) { PyErr_NoMemory(); goto fail; }
+    /* 1. every container, by the GIL holder (items of the row lists are NULL until step 2) */
     for (Py_ssize_t q = 0; q < nq; q++) {
         PyObject* row = PyList_New(k);
         if (!row) goto fail;
-        /* the row list is owned by `out` (or its tuple) from here on, so `goto fail` frees it */
         PyObject* entry = row;
         if (fast_scores) {
             PyObject* s = PySequence_Fast_GET_ITEM(fast_scores, q);
@@ -65,51 +191,61 @@ static PyObject* map_ids(PyObject* self, PyObject* args) {
             PyTuple_SET_ITEM(entry, 0, row);
             PyTuple_SET_ITEM(entry, 1, s);
         }
-        PyList_SET_ITEM(out, q, entry);
-        const Py_ssize_t base = q * k;
-        for (Py_ssize_t j = 0; j < k; j++) {
-            const Py_ssize_t t = base + j;
-            /* `ids` cannot change under us: the GIL is held and PyObject_Str of a non-str id is
-             * the only call-out; ob_item is re-read after it */
-            PyObject** items = ((PyListObject*)ids)->ob_item;
-            if (t + PF_FAR < total) {
-                const Py_ssize_t f = norm_row(r[t + PF_FAR], n);
-                if ((size_t)f < (size_t)n) __builtin_prefetch(items + f, 0, 0);
-            }
-            if (t + PF_NEAR < total) {
-                const Py_ssize_t f = norm_row(r[t + PF_NEAR], n);
-                if ((size_t)f < (size_t)n) __builtin_prefetch(items[f], 1, 0);
-            }
-            const Py_ssize_t i = norm_row(r[t], n);
-            if ((size_t)i >= (size_t)PyList_GET_SIZE(ids)) {
-                PyErr_SetString(PyExc_IndexError, "list index out of range");
-                goto fail;
-            }
-            PyObject* item = items[i];
-            PyObject* s;
-            if (PyUnicode_CheckExact(item)) {
-                Py_INCREF(item);
-                s = item;
-            } else {
-                s = PyObject_Str(item);
+        PyList_SET_ITEM(out, q, entry);      /* `out` owns the row from here on: `goto fail` frees it */
+        row_lists[q] = row;
+    }
+    /* 2. the gather (this thread + helpers; no interpreter calls inside) */
+    job_t jb;
+    jb.items = ((PyListObject*)ids)->ob_item;
+    jb.n = PyList_GET_SIZE(ids);
+    jb.rows = (const int64_t*)rows.buf;
+    jb.row_lists = row_lists;
+    jb.nq = nq; jb.k = k; jb.bad = 0; jb.leftover = 0;
+    run_job(&jb);
+    if (jb.bad) {
+        PyErr_SetString(PyExc_IndexError, "list index out of range");
+        goto fail;                           /* list_dealloc skips the slots that are still NULL */
+    }
+    /* 3. ids that are not exact `str`: str(id), like the reference */
+    if (jb.leftover) {
+        const int64_t* r = (const int64_t*)rows.buf;
+        for (Py_ssize_t q = 0; q < nq; q++) {
+            PyObject** dst = ((PyListObject*)row_lists[q])->ob_item;
+            for (Py_ssize_t j = 0; j < k; j++) {
+                if (dst[j]) continue;
+                const Py_ssize_t n_now = PyList_GET_SIZE(ids);       /* PyObject_Str may run Python code */
+                const Py_ssize_t i = norm_row(r[q * k + j], n_now);
+                if ((size_t)i >= (size_t)n_now) {
+                    PyErr_SetString(PyExc_IndexError, "list index out of range");
+                    goto fail;
+                }
+                PyObject* s = PyObject_Str(((PyListObject*)ids)->ob_item[i]);
                 if (!s) goto fail;
+                dst[j] = s;
             }
-            PyList_SET_ITEM(row, j, s);
         }
     }
+    free(row_lists);
     Py_XDECREF(fast_scores);
     PyBuffer_Release(&rows);
     return out;
 fail:
+    free(row_lists);
     Py_XDECREF(out);
     Py_XDECREF(fast_scores);
     PyBuffer_Release(&rows);
     return NULL;
 }
 
+static PyObject* map_threads(PyObject* self, PyObject* noargs) {
+    (void)self; (void)noargs;
+    return PyLong_FromLong(pool_threads());
+}
+
 static PyMethodDef methods[] = {
     {"map_ids", map_ids, METH_VARARGS,
      "map_ids(ids, rows_int64_buffer, nq, k, scores_or_None) -> [(list[str], scores[i]), ...]"},
+    {"map_threads", map_threads, METH_NOARGS, "number of threads map_ids uses for large inputs"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_b2ip_hostmap",

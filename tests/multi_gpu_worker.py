@@ -42,26 +42,31 @@ for k in (10, 100, 1000):
 
 # owner mode + global threshold round: every rank holds the global answer of the queries it owns;
 # with the threshold round each rank rescores about k/world rows instead of k + a window
+nq_big = 2500                                        # > 2048: the threshold round is used from here on
+q_big = torch.from_numpy(synth(nq_big, d, 777)).cuda()
 for k in (10, 100, 1000):
-    Dw, Iw = whole.search(qd, k)
-    for gthr in (True, False):
-        idx = ShardedIndex(d, device=local)
-        idx.global_threshold = gthr
-        lo, hi = shard_bounds(n, world, rank)
-        idx.add_local(x[lo:hi], lo)
-        D, I, (qlo, qhi) = idx.search_owned(qd, k)
-        assert (qlo, qhi) == shard_bounds(nq, world, rank) and D.shape == (qhi - qlo, k)
-        assert torch.equal(I, Iw[qlo:qhi]) and torch.equal(D, Dw[qlo:qhi]), f"k={k} gthr={gthr}: owned slice differs"
-        st = idx.engine.stats()
-        assert st["bound_violations"] == 0 and st["max_err_over_eps"] < 1.0
-        resc = st["rescored"] / nq
-        if gthr:
-            assert idx.exchange_searches == 1
-            resc_with = resc
-        else:
-            assert resc_with <= resc, (k, resc_with, resc)
-        D2, I2 = idx.search(qd, k)                       # the all-ranks form over the same buffers
-        assert torch.equal(I2, Iw) and torch.equal(D2, Dw)
+    for queries, nqs in ((qd, nq), (q_big, nq_big)):
+        Dw, Iw = whole.search(queries, k)
+        for gthr in (True, False):
+            idx = ShardedIndex(d, device=local)
+            idx.global_threshold = gthr
+            lo, hi = shard_bounds(n, world, rank)
+            idx.add_local(x[lo:hi], lo)
+            D, I, (qlo, qhi) = idx.search_owned(queries, k)
+            assert (qlo, qhi) == shard_bounds(nqs, world, rank) and D.shape == (qhi - qlo, k)
+            assert torch.equal(I, Iw[qlo:qhi]) and torch.equal(D, Dw[qlo:qhi]), f"k={k} gthr={gthr}: owned slice differs"
+            st = idx.engine.stats()
+            assert st["bound_violations"] == 0 and st["max_err_over_eps"] < 1.0
+            resc = st["rescored"] / nqs
+            if gthr:
+                assert idx.exchange_searches == 1
+                resc_with = resc
+            elif nqs > 2048 and k >= 100:
+                assert resc_with < resc, (k, resc_with, resc)    # the global bound prunes the rescore
+            else:
+                assert resc_with <= resc, (k, resc_with, resc)
+            D2, I2 = idx.search(queries, k)                   # the all-ranks form over the same buffers
+            assert torch.equal(I2, Iw) and torch.equal(D2, Dw)
     # host buffers in, this rank's slice out (the e2e call of bench.py at N > 1)
     Dh = np.full((nq, k), np.nan, np.float32); Ih = np.full((nq, k), -7, np.int64)
     for qq in (q, q.astype(np.float16)):

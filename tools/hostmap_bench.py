@@ -15,7 +15,10 @@ t = time.perf_counter(); arr = np.array(ids, dtype=object); t1 = time.perf_count
 t = time.perf_counter(); db = arr[I].tolist(); res = [(db[i], D[i]) for i in range(nq)]; t2 = time.perf_counter() - t
 print(f"numpy: object array {t1:.2f}s, map {t2:.3f}s")
 del db, res
+print("threads", hm.map_threads())
+res2 = None
 for rep in range(3):
+    res2 = None                                   # free the previous result outside the timed call
     t = time.perf_counter(); res2 = hm.map_ids(ids, I, nq, k, list(D)); t3 = time.perf_counter() - t
     print(f"hostmap.map_ids {t3:.3f}s  ({nq*k/t3/1e6:.1f} M ids/s)")
 assert res2[5][0] == [ids[i] for i in I[5]] and res2[5][1] is not None and len(res2) == nq
