@@ -516,6 +516,34 @@ def test_hostmap_builds_the_reference_result_objects(built):
     assert hm.map_ids(["a"], np.zeros((0, 4), dtype=np.int64), 0, 4, []) == []
 
 
+def test_hostmap_keeps_the_garbage_collector_out_of_the_way(built):
+    """map_ids switches the cyclic collector off while it allocates its 2*nq containers (every
+    full collection would walk the whole id list) and puts it back as it found it, also on the
+    error path; list[str] rows and (list[str], ndarray) tuples leave the collector's lists, rows
+    that hold anything else than exact `str` ids stay tracked."""
+    import gc
+    hm = built.load_hostmap()
+    ids = [f"doc{i}" for i in range(50)]
+    I = np.arange(12, dtype=np.int64).reshape(3, 4)
+    D = np.zeros((3, 4), np.float32)
+    was = gc.isenabled()
+    try:
+        for state in (True, False):
+            gc.enable() if state else gc.disable()
+            got = hm.map_ids(ids, I, 3, 4, list(D))
+            assert gc.isenabled() == state
+            assert not any(gc.is_tracked(t) or gc.is_tracked(t[0]) for t in got)
+            with pytest.raises(IndexError):
+                hm.map_ids(ids, I + 48, 3, 4, list(D))
+            assert gc.isenabled() == state
+        got = hm.map_ids(ids, I, 3, 4, [[0.0]] * 3)                  # tracked score rows: tuples stay tracked
+        assert all(gc.is_tracked(t) and not gc.is_tracked(t[0]) for t in got)
+        got = hm.map_ids(list(range(50)), I, 3, 4, None)             # str(id) path: rows stay tracked
+        assert all(gc.is_tracked(r) for r in got)
+    finally:
+        gc.enable() if was else gc.disable()
+
+
 def test_search_knn_chunk_pipeline_equals_one_search(built, monkeypatch):
     """search_knn searches in chunks on a background thread and maps ids chunk by chunk: any
     chunk size gives the result of one whole search, for numpy and (CPU) torch queries."""

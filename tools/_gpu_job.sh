@@ -1,12 +1,4 @@
-K='regex:coarse_|finalize_kernel|refresh_threshold|prep_queries|merge_topk|exchange_|shadow_rows|fill_'
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2p_bench_plain.json 2> gpurun_out/r2p_bench_plain.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --csv --log-file gpurun_out/r2_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2p_bench_ncu.json 2> gpurun_out/r2p_bench_ncu.err; wc -l gpurun_out/r2_bench_launches.csv
-export B2IP_GRAPH=0
-ncu --set full --import-source on --clock-control none -k regex:coarse_filter_pair -s 3 -c 1 -f -o gpurun_out/r2_pair_c3shard python tools/regimes.py --n-corpus 2625000 --cases 100000:100 --reps 0 > gpurun_out/r2p_ncu_pair.log 2>&1; tail -1 gpurun_out/r2p_ncu_pair.log | cut -c1-120
-ncu --set full --import-source on --clock-control none -k regex:coarse_stream -s 2 -c 1 -f -o gpurun_out/r2_stream_c5 python tools/regimes.py --n-corpus 21000000 --cases 64:10 --reps 0 > gpurun_out/r2p_ncu_stream.log 2>&1; tail -1 gpurun_out/r2p_ncu_stream.log | cut -c1-120
-ncu --set full --import-source on --clock-control none -k regex:finalize_kernel -c 1 -f -o gpurun_out/r2_finalize_k100_f32 python tools/regimes.py --n-corpus 2625000 --cases 100000:100 --reps 0 > gpurun_out/r2p_ncu_fin.log 2>&1; tail -1 gpurun_out/r2p_ncu_fin.log | cut -c1-120
-ncu --set full --import-source on --clock-control none -k regex:refresh_threshold -s 2 -c 1 -f -o gpurun_out/r2_refresh_k100_f32 python tools/regimes.py --n-corpus 2625000 --cases 100000:100 --reps 0 > gpurun_out/r2p_ncu_ref.log 2>&1; tail -1 gpurun_out/r2p_ncu_ref.log | cut -c1-120
-M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum,lts__t_sector_hit_rate.pct,sm__cycles_elapsed.avg.per_second
-for gx in 37 74 148; do B2IP_GX=$gx ncu --metrics $M --clock-control none -k regex:coarse_filter_pair -s 3 -c 1 --csv --log-file gpurun_out/r2_pair_l2_gx$gx.csv python tools/regimes.py --n-corpus 2625000 --cases 100000:100 --reps 0 > /dev/null 2>&1; done
-python tools/tune_coarse.py --n-corpus 2625000 --sweep "gx=74;gx=37;gx=148;gx=111;gx=74" --reps 3 > gpurun_out/r2_tune_gx.log 2>&1; cat gpurun_out/r2_tune_gx.log
-ls -la gpurun_out/*.ncu-rep gpurun_out/r2_pair_l2_gx*.csv | cut -c25-120
+python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2q_ref.json 2> gpurun_out/r2q_ref.err; tail -c 400 gpurun_out/r2q_ref.err; python -c "
+import json; l=json.loads(open('gpurun_out/r2q_ref.json').read().strip().splitlines()[-1]); print(l['value'], l['ms_per_step'], l['cpu_baseline']['sample'][:200], l['cpu_baseline']['gflops'], l['cpu_baseline']['corpus_to_host_s'])"
+python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2q_bench1.json 2> gpurun_out/r2q_bench1.err; tail -c 600 gpurun_out/r2q_bench1.err; python tools/show_bench.py gpurun_out/r2q_bench1.json
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
