@@ -28,6 +28,7 @@
 #include "../../include/b2ip.h"
 #include "coarse_kernel.cuh"
 #include "select_kernels.cuh"
+#include "stream_search.cuh"
 
 using namespace b2ip;
 
@@ -100,7 +101,7 @@ struct b2ip_index_s {
     PFN_encodeTiled encode = nullptr;
     // grow-only workspace
     DevBuf q16, eps2, thr, cnt, kept, flags, cand, qstage, qhalf, out_s, out_r, exact_scores, exact_misc,
-        qlist, stage, seg_tab;
+        qlist, stage, seg_tab, stream_sync;
     int n_seg = 0;                        // row segments (b2ip_set_row_segments); 0 = row_offset
     std::vector<cudaEvent_t> ev_pool, ev_fin;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
@@ -112,6 +113,12 @@ struct b2ip_index_s {
     int verbose = 0;
     int pair = 1;                         // CTA-pair (cta_group::2) scoring kernel when nq > 128
     int stream_kernel = 1;                // nq <= 64: streaming kernel (corpus on the MMA's M side)
+    int stream_coop = 1;                  // cooperative launch of that kernel (co-residency guaranteed)
+    int stream_stages = 8;                // cap on the corpus stages in flight per SM (tuning)
+    int stream_fused = 0;                 // ... with the whole slab schedule + threshold refreshes in ONE launch
+                                          // (stream_search.cuh).  OFF by default: measured, it saves the launch
+                                          // structure (-35 us per batch) but streams 3-4 % slower -- see DESIGN 4.1d
+    long long stream_timeout_ns = 2ll * 1000000000ll;   // bound on every in-kernel wait of that launch
     int dense_first = 1;                  // first slab stored positionally (no counters / hit extraction)
     int fuse_refresh = 1;                 // last threshold refresh inside the finalize kernel
     int two_stage = 1;                    // finalize rescoring in two stages (window eps instead of 2 eps)
@@ -650,6 +657,32 @@ int enqueue_exchange(b2ip_handle h, int64_t nq, int k, const DynArgs* dyn = null
 }
 
 // ------------------------------------------------------------------------- tensor path
+// Slab sizes of the FIXED geometric schedule of the latency regime (<= 2048 queries): the sequence
+// the launch loop of tensor_search walks through, computed up front for the one-launch streaming
+// search (stream_search.cuh).  `slab` = size of the first slab.
+void plan_fixed_slabs(int64_t n, int64_t slab, int cap, int k, std::vector<int64_t>* out) {
+    out->clear();
+    double growth = 0.0;
+    if (n > slab) {
+        const double r_max = std::max(2.0, 0.5 * cap / (3.0 * k));
+        const double span = static_cast<double>(n) / static_cast<double>(slab);
+        const int steps = std::max(1, static_cast<int>(std::ceil(std::log(span) / std::log(r_max))));
+        growth = std::pow(span, 1.0 / steps);
+    }
+    int64_t done = 0;
+    while (done < n) {
+        int64_t s = std::min<int64_t>(slab, n - done);
+        if (done + s < n) s = std::max<int64_t>(TILE_X, s / TILE_X * TILE_X);
+        s = std::min<int64_t>(s, n - done);
+        out->push_back(s);
+        done += s;
+        if (done >= n) break;
+        if (out->size() > 64) { out->clear(); return; }
+        slab = std::max<int64_t>(TILE_X, static_cast<int64_t>(static_cast<double>(done) * (growth - 1.0)));
+        if (n - done - slab < slab / 4) slab = n - done;          // no tiny tail slab
+    }
+}
+
 int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_scores,
                   int64_t* d_rows) {
     const int64_t n = h->n;
@@ -768,13 +801,6 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         slab = slab / TILE_X * TILE_X;
         const int64_t first_slab = std::min<int64_t>(slab, n);
         const bool dense_first = h->dense_first != 0;
-        prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, h->stream>>>(
-            qptr, reinterpret_cast<__nv_bfloat16*>(h->q16.p), nqb, h->d, h->d_pad, h->norm_stats,
-            reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
-            reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p),
-            reinterpret_cast<int*>(h->flags.p), h->sh, nq_pad, h->gstats,
-            dense_first ? static_cast<int>(first_slab) : 0, dyn);
-        h->stats.total_launches++;
         CUtensorMap tmap_q;
         CAP_RC(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, TILE_Q));
         const bool use_pair = h->pair && nqb > TILE_Q && h->sm_count >= 2;
@@ -783,11 +809,39 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         const int nq_s = nqb <= 32 ? 32 : 64;
         const size_t q_bytes = static_cast<size_t>(h->d_pad / KBLOCK_ELEMS) * nq_s * KBLOCK_BYTES;
         const int stream_stages = static_cast<int>(std::min<long long>(
-            STREAM_MAX_STAGES,
+            std::min(STREAM_MAX_STAGES, h->stream_stages),
             (static_cast<long long>(MAX_SMEM_OPTIN) - STREAM_MISC_BYTES - static_cast<long long>(q_bytes)) / STREAM_X_STAGE_BYTES));
         const bool use_stream = h->stream_kernel && nqb <= 64 && stream_stages >= 4;
         const size_t stream_smem = static_cast<size_t>(std::max(stream_stages, 0)) * STREAM_X_STAGE_BYTES + q_bytes + STREAM_MISC_BYTES;
         if (use_stream) CAP_RC(make_tmap_bf16(h, &tmap_q, h->q16.p, pad_q(nqb), h->d_pad, nq_s));
+        // ... and the whole slab schedule in one launch (stream_search.cuh) when it is known up
+        // front (it is for <= 2048 queries), has at most STREAM_MAX_SLABS slabs, and the in-kernel
+        // refresh's staging fits next to >= 4 corpus stages
+        const int fused_stages = static_cast<int>(std::min<long long>(
+            std::min(STREAM_MAX_STAGES, h->stream_stages),
+            (static_cast<long long>(MAX_SMEM_OPTIN) - STREAM_MISC_BYTES - STREAM_REFRESH_BYTES - static_cast<long long>(q_bytes)) / STREAM_X_STAGE_BYTES));
+        StreamSearchParams ssp{};
+        bool fused_stream = use_stream && h->stream_fused && !h->dbg && fused_stages >= 4 && nqb <= h->sm_count;
+        if (fused_stream) {
+            std::vector<int64_t> sizes;
+            plan_fixed_slabs(n, slab, cap, k, &sizes);
+            if (sizes.empty() || sizes.size() > static_cast<size_t>(STREAM_MAX_SLABS)) {
+                fused_stream = false;
+            } else {
+                ssp.n_slabs = static_cast<int>(sizes.size());
+                ssp.slab_row[0] = 0;
+                for (size_t i = 0; i < sizes.size(); i++) ssp.slab_row[i + 1] = ssp.slab_row[i] + sizes[i];
+                CAP_RC(ensure(h, h->stream_sync, STREAM_SYNC_WORDS * sizeof(unsigned int)));
+            }
+        }
+        prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, h->stream>>>(
+            qptr, reinterpret_cast<__nv_bfloat16*>(h->q16.p), nqb, h->d, h->d_pad, h->norm_stats,
+            reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
+            reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p),
+            reinterpret_cast<int*>(h->flags.p), h->sh, nq_pad, h->gstats,
+            dense_first ? static_cast<int>(first_slab) : 0, dyn,
+            fused_stream ? reinterpret_cast<unsigned int*>(h->stream_sync.p) : nullptr);
+        h->stats.total_launches++;
 
         CoarseParams cp{};
         cp.num_k_blocks = h->d_pad / KBLOCK_ELEMS;
@@ -826,6 +880,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             s = std::min<int64_t>(s, std::max<int64_t>(1, (1ll << 30) / std::max(1, cp.q_tiles)) * STREAM_TILE_X);
             if (done + s < n) s = std::max<int64_t>(TILE_X, s / TILE_X * TILE_X);
             s = std::min<int64_t>(s, n - done);
+            if (fused_stream) s = n;             // every slab of the schedule in this one launch
             cp.x_row0 = done;
             cp.x_row_end = done + s;
             cp.x_tiles = use_stream ? static_cast<int>((s + STREAM_TILE_X - 1) / STREAM_TILE_X)
@@ -835,7 +890,51 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
             cudaEvent_t e0 = get_event(h, ev_used++), e1 = get_event(h, ev_used++);
             CAP_TRY(rec(e0));
-            if (use_stream) {
+            if (fused_stream) {
+                long long max_tiles = 1;
+                for (int i = 0; i < ssp.n_slabs; i++)
+                    max_tiles = std::max<long long>(max_tiles, (ssp.slab_row[i + 1] - ssp.slab_row[i] + STREAM_TILE_X - 1) / STREAM_TILE_X);
+                // the first nqb CTAs refresh one query each between slabs: the grid holds at least that many
+                const int grid = static_cast<int>(std::min<long long>(std::max<long long>(max_tiles, nqb), h->sm_count));
+                ssp.dense_first = dense_first ? 1 : 0;
+                ssp.k = k;
+                ssp.thr = reinterpret_cast<float*>(h->thr.p);
+                ssp.kept = reinterpret_cast<int*>(h->kept.p);
+                ssp.eps2 = reinterpret_cast<const float*>(h->eps2.p);
+                ssp.flags = reinterpret_cast<int*>(h->flags.p);
+                ssp.gstats = h->gstats;
+                ssp.sync = reinterpret_cast<unsigned int*>(h->stream_sync.p);
+                ssp.timeout_ns = h->stream_timeout_ns;
+                cp.x_tiles = static_cast<int>(max_tiles);
+                // cooperative launch: the CTAs wait for each other between slabs, so the grid must be
+                // co-resident even when another stream / process shares the GPU
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(static_cast<unsigned int>(grid));
+                cfg.blockDim = dim3(COARSE_THREADS);
+                cfg.dynamicSmemBytes = static_cast<size_t>(fused_stages) * STREAM_X_STAGE_BYTES + q_bytes +
+                                       STREAM_MISC_BYTES + STREAM_REFRESH_BYTES;
+                cfg.stream = h->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeCooperative;
+                at[0].val.cooperative = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = h->stream_coop ? 1 : 0;
+                const cudaError_t le =
+                    nq_s == 32 ? cudaLaunchKernelEx(&cfg, coarse_stream_search_kernel<32>, tmap_q, tmap_x_pair, cp, ssp, fused_stages)
+                               : cudaLaunchKernelEx(&cfg, coarse_stream_search_kernel<64>, tmap_q, tmap_x_pair, cp, ssp, fused_stages);
+                if (le != cudaSuccess) {
+                    // not launchable here (e.g. an SM partition smaller than the grid): per-slab launches from now on
+                    abort_capture();
+                    cudaGetLastError();
+                    if (h->verbose) fprintf(stderr, "[b2ip] one-launch streaming search unavailable (%s): per-slab launches\n", cudaGetErrorString(le));
+                    h->stream_fused = 0;
+                    h->opt_gen++;
+                    CU_TRY(h, cudaStreamSynchronize(h->stream));
+                    memset(&h->stats, 0, sizeof(h->stats));
+                    h->stats.nq = nq; h->stats.ntotal = h->n; h->stats.k = k; h->stats.mode_used = B2IP_MODE_TENSOR;
+                    return tensor_search(h, q32, nq, k, d_scores, d_rows);
+                }
+            } else if (use_stream) {
                 const int grid = static_cast<int>(std::min<long long>(cp.x_tiles, h->sm_count));
                 if (nq_s == 32)
                     coarse_stream_kernel<32><<<grid, COARSE_THREADS, stream_smem, h->stream>>>(
@@ -873,7 +972,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             CAP_TRY(rec(e2));
             h->stats.coarse_launches++;
             h->stats.total_launches += fused ? 1 : 2;
-            h->stats.slabs++;
+            h->stats.slabs += fused_stream ? ssp.n_slabs : 1;
             h->stats.coarse_flops += 2.0 * nqb * static_cast<double>(s) * h->d;
             done += s;
             if (last) break;
@@ -1196,6 +1295,8 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
             cudaFuncSetAttribute(coarse_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_stream_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_stream_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
+            cudaFuncSetAttribute(coarse_stream_search_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
+            cudaFuncSetAttribute(coarse_stream_search_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
             cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
             cudaFuncSetAttribute(finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
             cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1206,6 +1307,7 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
                                             // the corpus tiles of a group stay L2 resident (measured best)
     if (const char* s = getenv("B2IP_GX")) h->gx = std::max(1, atoi(s));
     if (const char* s = getenv("B2IP_STREAM_KERNEL")) h->stream_kernel = atoi(s);
+    if (const char* s = getenv("B2IP_STREAM_FUSED")) h->stream_fused = atoi(s);
     if (const char* s = getenv("B2IP_HINT_Q")) h->hint_q = atoi(s);
     if (const char* s = getenv("B2IP_HINT_X")) h->hint_x = atoi(s);
     if (const char* s = getenv("B2IP_CAND_BUDGET_MB")) h->cand_budget_bytes = std::max(1ll, atoll(s)) << 20;
@@ -1274,6 +1376,10 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "pair") h->pair = static_cast<int>(value);
     else if (n == "dense_first") h->dense_first = static_cast<int>(value);
     else if (n == "stream_kernel") h->stream_kernel = static_cast<int>(value);
+    else if (n == "stream_fused") h->stream_fused = static_cast<int>(value);
+    else if (n == "stream_coop") h->stream_coop = static_cast<int>(value);
+    else if (n == "stream_stages") h->stream_stages = std::max(4, static_cast<int>(value));
+    else if (n == "stream_timeout_ms") h->stream_timeout_ns = std::max<int64_t>(1, value) * 1000000ll;
     else if (n == "fuse_refresh") h->fuse_refresh = static_cast<int>(value);
     else if (n == "two_stage") h->two_stage = static_cast<int>(value);
     else if (n == "cand_budget_mb") h->cand_budget_bytes = std::max<int64_t>(1, value) << 20;

@@ -509,10 +509,10 @@ coarse_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 //                     per-query thresholds held in registers
 // =======================================================================================
 constexpr int STREAM_TILE_X = 128;
-constexpr int STREAM_MAX_STAGES = 8;
+constexpr int STREAM_MAX_STAGES = 12;
 constexpr int STREAM_ACC = 4;
 constexpr int STREAM_X_STAGE_BYTES = STREAM_TILE_X * KBLOCK_BYTES;   // 16 KiB
-constexpr int STREAM_MISC_BYTES = 1024 /*align*/ + 256 /*barriers*/;
+constexpr int STREAM_MISC_BYTES = 1024 /*align*/ + 320 /*barriers*/;
 
 template <int NQ>
 __global__ void __launch_bounds__(COARSE_THREADS, 1)

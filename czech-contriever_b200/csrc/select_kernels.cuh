@@ -257,11 +257,15 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
                                     int* __restrict__ cnt, int* __restrict__ kept,
                                     int* __restrict__ flags, int sh, int nq_pad,
                                     long long* __restrict__ gstats, int init_cnt,
-                                    const DynArgs* __restrict__ dyn) {
+                                    const DynArgs* __restrict__ dyn,
+                                    unsigned int* __restrict__ stream_sync = nullptr) {
     if (dyn) q32 = dyn->q32;
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x < GS_COUNT && gstats) gstats[threadIdx.x] = 0;
+    // arrival counter, abort word and per-query threshold epochs of the one-launch streaming search
+    if (stream_sync && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 2 + 64; i += blockDim.x) stream_sync[i] = 0u;
     if (q >= nq) {
         // rows that pad the last (pair) tile: zeros, so no TMA box hangs over the tensor's end
         if (q < nq_pad) {
@@ -306,6 +310,27 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
 }
 
 // ---------------------------------------------------------------------------------------
+// thread groups the selection routines run on
+// ---------------------------------------------------------------------------------------
+// The whole CTA (refresh / finalize kernels), or a contiguous range of its warps on a named
+// barrier: the four epilogue warps of the multi-slab streaming kernel (stream_search.cuh) refresh
+// the thresholds between slabs while the TMA and MMA warps of the same CTA keep streaming.
+struct CtaGroup {
+    static __device__ __forceinline__ int tid() { return static_cast<int>(threadIdx.x); }
+    static __device__ __forceinline__ int size() { return static_cast<int>(blockDim.x); }
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+template <int kFirstThread, int kThreads, int kBarrier>
+struct WarpRangeGroup {
+    static_assert(kFirstThread % 32 == 0 && kThreads % 32 == 0 && kThreads <= SEL_THREADS && kBarrier > 0, "whole warps");
+    static __device__ __forceinline__ int tid() { return static_cast<int>(threadIdx.x) - kFirstThread; }
+    static __device__ __forceinline__ int size() { return kThreads; }
+    static __device__ __forceinline__ void sync() {
+        asm volatile("bar.sync %0, %1;" ::"n"(kBarrier), "n"(kThreads) : "memory");
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // block-wide radix select
 // ---------------------------------------------------------------------------------------
 // Top `n_bytes` bytes of the k-th largest of keys[0..n) (1 <= k <= n); low bytes are zero.
@@ -314,6 +339,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ q32, __nv_bfloat16
 // mantissa bits (the bound is at most 2^-15 relative below the true value, ~1/500 of the error
 // margin it is combined with) and saves a pass.  first_pass / prefix0: leading bytes all keys are
 // known to share (see common_prefix_bytes) are not counted again.
+template <class G = CtaGroup>
 __device__ unsigned long long block_radix_select(const unsigned long long* __restrict__ keys,
                                                  int n, int k, int n_bytes, unsigned int* hist,
                                                  unsigned long long* s_prefix, int* s_krem,
@@ -322,13 +348,13 @@ __device__ unsigned long long block_radix_select(const unsigned long long* __res
     int krem = k;
     for (int pass = first_pass; pass < n_bytes; pass++) {
         const int shift = 56 - 8 * pass;
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
+        for (int i = G::tid(); i < 256; i += G::size()) hist[i] = 0;
+        G::sync();
         const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
         // Scores of one list share their leading bytes, so most lanes of a warp hit the SAME bin:
         // lanes with equal digits elect one of them to add the whole group's count.
-        for (int base = 0; base < n; base += blockDim.x) {
-            const int i = base + threadIdx.x;
+        for (int base = 0; base < n; base += G::size()) {
+            const int i = base + G::tid();
             unsigned int digit = 256u;                       // 256 = not counted
             if (i < n) {
                 const unsigned long long key = keys[i];
@@ -338,15 +364,15 @@ __device__ unsigned long long block_radix_select(const unsigned long long* __res
             // counted by lane 0 in one add, the rest add for themselves
             const unsigned int first = __shfl_sync(0xffffffffu, digit, 0);
             const unsigned int same = __ballot_sync(0xffffffffu, digit == first);
-            if ((threadIdx.x & 31) == 0) {
+            if ((G::tid() & 31) == 0) {
                 if (digit < 256u) atomicAdd(&hist[digit], static_cast<unsigned int>(__popc(same)));
             } else if (digit < 256u && digit != first) {
                 atomicAdd(&hist[digit], 1u);
             }
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
+        G::sync();
+        if (G::tid() < 32) {
+            const int lane = G::tid();
             unsigned int c[8], sum = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) { c[j] = hist[255 - (8 * lane + j)]; sum += c[j]; }
@@ -369,7 +395,7 @@ __device__ unsigned long long block_radix_select(const unsigned long long* __res
                 *s_krem = static_cast<int>(r);
             }
         }
-        __syncthreads();
+        G::sync();
         prefix = *s_prefix;
         krem = *s_krem;
     }
@@ -378,12 +404,13 @@ __device__ unsigned long long block_radix_select(const unsigned long long* __res
 
 // In-place stream compaction of keys[0..n): keeps keys whose high word is > hi_thr
 // (or, with by_key, keys >= key_thr).  Returns the number kept (all threads).
+template <class G = CtaGroup>
 __device__ int block_compact(const unsigned long long* keys, int n, bool by_key, uint32_t hi_thr,
                              unsigned long long key_thr, unsigned long long* out, int* s_warp) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = G::tid() & 31, warp = G::tid() >> 5, nw = G::size() >> 5;
     int base_out = 0;
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int i = base + threadIdx.x;
+    for (int base = 0; base < n; base += G::size()) {
+        const int i = base + G::tid();
         unsigned long long key = 0;
         bool keep = false;
         if (i < n) {
@@ -392,7 +419,7 @@ __device__ int block_compact(const unsigned long long* keys, int n, bool by_key,
         }
         const unsigned int ballot = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_warp[warp] = __popc(ballot);
-        __syncthreads();
+        G::sync();
         int off = 0, tot = 0;
         for (int w = 0; w < nw; w++) {
             const int c = s_warp[w];
@@ -401,17 +428,18 @@ __device__ int block_compact(const unsigned long long* keys, int n, bool by_key,
         }
         if (keep) out[base_out + off + __popc(ballot & ((1u << lane) - 1u))] = key;
         base_out += tot;
-        __syncthreads();
+        G::sync();
     }
     return base_out;
 }
 
 // Same selection, for `out` NOT aliasing `keys`: each warp owns a contiguous segment, one
 // counting pass, one block barrier, one writing pass (2 barriers instead of 2 per 256 keys).
+template <class G = CtaGroup>
 __device__ int block_compact_disjoint(const unsigned long long* keys, int n, bool by_key,
                                       uint32_t hi_thr, unsigned long long key_thr,
                                       unsigned long long* out, int* s_warp, bool invert = false) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = G::tid() & 31, warp = G::tid() >> 5, nw = G::size() >> 5;
     const int seg = ((n + nw - 1) / nw + 31) & ~31;
     const int b = warp * seg, e = min(n, b + seg);
     int mine = 0;
@@ -426,7 +454,7 @@ __device__ int block_compact_disjoint(const unsigned long long* keys, int n, boo
         mine += __popc(__ballot_sync(0xffffffffu, keep));
     }
     if (lane == 0) s_warp[warp] = mine;
-    __syncthreads();
+    G::sync();
     int off = 0, tot = 0;
     for (int w = 0; w < nw; w++) {
         const int c = s_warp[w];
@@ -446,7 +474,7 @@ __device__ int block_compact_disjoint(const unsigned long long* keys, int n, boo
         if (keep) out[off + __popc(ballot & ((1u << lane) - 1u))] = key;
         off += __popc(ballot);
     }
-    __syncthreads();
+    G::sync();
     return tot;
 }
 
@@ -457,22 +485,23 @@ __device__ int block_compact_disjoint(const unsigned long long* keys, int n, boo
 // so every member of the final exact top-k has exact >= c_k - eps and coarse >= c_k - 2 eps:
 // rows below that can be dropped for good, and later slabs only need to report above it.
 // Returns the number of entries the list holds afterwards (block-uniform), or -1 when the query
-// overflowed its list (flagged for the exact path).  `scratch` = REFRESH_SMEM_KEYS keys of
-// shared memory: lists that fit are pulled into it once, so the 4 select passes and the
-// compaction never touch L2 again.
+// overflowed its list (flagged for the exact path).  `scratch` = `scratch_keys` keys of
+// shared memory: lists that fit are pulled into it once, so the select passes and the
+// compaction never touch L2 again.  G = the threads that run it (see CtaGroup).
+template <class G = CtaGroup>
 __device__ int refresh_list(int q, int k, int cap, unsigned long long* __restrict__ cand,
                             int* __restrict__ cnt, int* __restrict__ kept, float* __restrict__ thr,
                             const float* __restrict__ eps2, int* __restrict__ flags,
                             long long* __restrict__ gstats, unsigned long long* scratch,
                             unsigned int* hist, unsigned long long* s_prefix, int* s_krem,
-                            int* s_warp) {
+                            int* s_warp, int scratch_keys = REFRESH_SMEM_KEYS) {
     const int n = cnt[q];
     const int prev = kept[q];
-    if (threadIdx.x == 0) { s_warp[0] = -1; s_warp[1] = 0; }   // AND / OR of the staged keys' high words
-    __syncthreads();                                 // everyone has read the counters
+    if (G::tid() == 0) { s_warp[0] = -1; s_warp[1] = 0; }   // AND / OR of the staged keys' high words
+    G::sync();                                 // everyone has read the counters
     if (n > cap) {
         // more hits than the list holds: this query is re-run on the exact path
-        if (threadIdx.x == 0) {
+        if (G::tid() == 0) {
             flags[q] |= FLAG_OVERFLOW;
             thr[q] = INFINITY;
             cnt[q] = 0;
@@ -482,22 +511,22 @@ __device__ int refresh_list(int q, int k, int cap, unsigned long long* __restric
         return -1;
     }
     if (n == prev) return n;
-    if (threadIdx.x == 0)
+    if (G::tid() == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(gstats + GS_CANDIDATES),
                   static_cast<unsigned long long>(n - prev));
     if (n < k) {
-        if (threadIdx.x == 0) kept[q] = n;
+        if (G::tid() == 0) kept[q] = n;
         return n;
     }
     unsigned long long* keys = cand + static_cast<long long>(q) * cap;
     const unsigned long long* src = keys;
     int first_pass = 0;
     unsigned long long prefix0 = 0ull;
-    if (n <= REFRESH_SMEM_KEYS) {
+    if (n <= scratch_keys) {
         // the scores of one list lie in a narrow range: the leading byte(s) they all share are
         // found while the list is staged (AND / OR of the high words) and skipped by the select
         unsigned int a = 0xFFFFFFFFu, o = 0u;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        for (int i = G::tid(); i < n; i += G::size()) {
             const unsigned long long key = keys[i];
             scratch[i] = key;
             a &= static_cast<unsigned int>(key >> 32);
@@ -505,27 +534,27 @@ __device__ int refresh_list(int q, int k, int cap, unsigned long long* __restric
         }
         a = __reduce_and_sync(0xffffffffu, a);
         o = __reduce_or_sync(0xffffffffu, o);
-        if ((threadIdx.x & 31) == 0) {
+        if ((G::tid() & 31) == 0) {
             atomicAnd(reinterpret_cast<unsigned int*>(&s_warp[0]), a);
             atomicOr(reinterpret_cast<unsigned int*>(&s_warp[1]), o);
         }
-        __syncthreads();
+        G::sync();
         src = scratch;
         const unsigned int ah = static_cast<unsigned int>(s_warp[0]), oh = static_cast<unsigned int>(s_warp[1]);
         const int common = (ah == oh) ? 32 : __clz(static_cast<int>(ah ^ oh));
         first_pass = min(common >> 3, 3);
         if (first_pass > 0)
             prefix0 = static_cast<unsigned long long>(ah & (0xFFFFFFFFu << (32 - 8 * first_pass))) << 32;
-        __syncthreads();                             // s_warp is reused by the compaction below
+        G::sync();                             // s_warp is reused by the compaction below
     }
-    const unsigned long long pk = block_radix_select(src, n, k, 3, hist, s_prefix, s_krem, first_pass, prefix0);
+    const unsigned long long pk = block_radix_select<G>(src, n, k, 3, hist, s_prefix, s_krem, first_pass, prefix0);
     const float ck = unorder_f32(static_cast<uint32_t>(pk >> 32));
     float t = __fsub_rd(ck, eps2[q]);
     if (!(t == t)) t = -INFINITY;                    // inf - inf: no usable threshold
     t = nextafterf(t, -INFINITY);                    // admission test is strict
-    const int m = (src == keys) ? block_compact(src, n, false, order_f32(t), 0ull, keys, s_warp)
-                                : block_compact_disjoint(src, n, false, order_f32(t), 0ull, keys, s_warp);
-    if (threadIdx.x == 0) {
+    const int m = (src == keys) ? block_compact<G>(src, n, false, order_f32(t), 0ull, keys, s_warp)
+                                : block_compact_disjoint<G>(src, n, false, order_f32(t), 0ull, keys, s_warp);
+    if (G::tid() == 0) {
         cnt[q] = m;
         kept[q] = m;
         thr[q] = t;

@@ -24,9 +24,9 @@ def fo():
     return flatip_oracle
 
 
-def _engine(x, device=0):
+def _engine(x, device=0, store="f32"):
     from b2ip import Engine
-    e = Engine(x.shape[1], device)
+    e = Engine(x.shape[1], device, store=store)
     e.add(x)
     return e
 
@@ -92,6 +92,41 @@ def test_small_query_batches_latency_regime(fo, nq, k):
     assert st["slabs"] >= 2 and st["fallback_queries"] == 0
     Do, Io = fo.search(q, x, k)
     fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+
+
+@pytest.mark.parametrize("nq,k,d,store", [(1, 10, 768, "f32"), (7, 10, 768, "f32"), (33, 100, 128, "f32"),
+                                          (64, 10, 768, "f32"), (64, 100, 1024, "f32"), (48, 10, 768, "f16"),
+                                          (64, 1000, 256, "bf16")])
+def test_one_launch_streaming_search_equals_per_slab_launches(fo, nq, k, d, store):
+    """Option stream_fused=1: batches of <= 64 queries run the whole slab schedule -- scoring AND the
+    threshold refreshes between slabs -- inside one persistent cooperative launch
+    (csrc/stream_search.cuh; opt-in).  It must reproduce the per-slab launch
+    sequence bit for bit: same thresholds, same candidate counts, same
+    rescored rows, same answer (and the oracle's)."""
+    x = synth(300_000, d, 99)
+    q = synth(nq, d, 100)
+    e = _engine(x, store=store)
+    e.set_option("graph", 0)
+    e.set_option("stream_fused", 1)
+    D1, I1 = e.search(q, k)
+    s1 = e.stats()
+    e.set_option("stream_fused", 0)
+    D0, I0 = e.search(q, k)
+    s0 = e.stats()
+    assert s1["coarse_launches"] == 1 and s0["coarse_launches"] == s0["slabs"] == s1["slabs"] >= 3
+    assert s1["fallback_queries"] == 0 and s0["fallback_queries"] == 0
+    assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
+    assert s1["candidates"] == s0["candidates"] and s1["rescored"] == s0["rescored"]
+    xs = e.export_rows(0, x.shape[0]) if store != "f32" else x       # the values actually stored
+    Do, Io = fo.search(q, xs, k)
+    fo.compare_topk(D1, I1, Do, Io, q, xs, rtol=RTOL)
+    # and replayed from a CUDA graph
+    e.set_option("stream_fused", 1)
+    e.set_option("graph", 1)
+    for it in range(3):
+        Dg, Ig = e.search(q, k)
+        assert np.array_equal(Ig, I1) and np.array_equal(Dg, D1)
+    assert e.stats()["graph_mode"] == 2 and e.stats()["coarse_launches"] == 1
 
 
 def test_small_batches_replay_a_cuda_graph(fo):

@@ -1,4 +1,6 @@
-python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2q_ref.json 2> gpurun_out/r2q_ref.err; tail -c 400 gpurun_out/r2q_ref.err; python -c "
-import json; l=json.loads(open('gpurun_out/r2q_ref.json').read().strip().splitlines()[-1]); print(l['value'], l['ms_per_step'], l['cpu_baseline']['sample'][:200], l['cpu_baseline']['gflops'], l['cpu_baseline']['corpus_to_host_s'])"
-python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2q_bench1.json 2> gpurun_out/r2q_bench1.err; tail -c 600 gpurun_out/r2q_bench1.err; python tools/show_bench.py gpurun_out/r2q_bench1.json
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 300 python tools/c5_latency.py --n-corpus 21000000 --iters 100 --fused 0,1,2,0,1,2 --stages 8 > gpurun_out/r2v_c5_21M.log 2>&1; cut -c1-250 gpurun_out/r2v_c5_21M.log
+export B2IP_GRAPH=0
+for f in 0 1; do
+B2IP_STREAM_FUSED=$f timeout 300 ncu --set full --import-source on --clock-control none -k regex:coarse_stream -c 6 -f -o gpurun_out/r2v_stream_fused$f python tools/regimes.py --n-corpus 21000000 --cases 64:10 --reps 0 > gpurun_out/r2v_ncu_$f.log 2>&1; tail -1 gpurun_out/r2v_ncu_$f.log | cut -c1-200
+done
+ls -la gpurun_out/r2v_*.ncu-rep
