@@ -402,6 +402,104 @@ __device__ unsigned long long block_radix_select(const unsigned long long* __res
     return prefix;
 }
 
+// LOWER BOUND of the k-th largest score word (high 32 bits) of skeys[0..n) in shared memory, for
+// 1 <= k <= n, given the smallest / largest score word of the list (kmin / kmax).  A threshold
+// needs no more than a lower bound, so instead of a byte-wise radix select (3 passes over the
+// list, each with its own scan) this takes ONE histogram pass of BOUND_BINS equal-width bins over
+// [kmin, kmax] -- the scores of a candidate list lie in a narrow range, so a bin is a few thousand
+// ulps wide -- and one cheap pass that splits the bin holding the k-th score into 256: the result
+// is within 2^(shift-8) key units (typically 32 ulps, 1e-6 relative) below the true value.
+// hist: BOUND_BINS words.  Ends with a barrier; s_prefix / s_krem / s_warp are free afterwards.
+constexpr int BOUND_BINS = 1024;
+
+template <class G = CtaGroup>
+__device__ uint32_t block_bound_select(const unsigned long long* skeys, int n, int k, uint32_t kmin,
+                                       uint32_t kmax, unsigned int* hist,
+                                       unsigned long long* s_prefix, int* s_krem, int* s_warp) {
+    if (kmin == kmax) return kmin;
+    const uint32_t range = kmax - kmin;
+    const int shift = max(0, 32 - __clz(static_cast<int>(range)) - 10);     // (range >> shift) < BOUND_BINS
+    const int tid = G::tid(), nt = G::size();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < BOUND_BINS; i += nt) hist[i] = 0;
+    G::sync();
+    for (int i = tid; i < n; i += nt) {
+        const uint32_t hi = static_cast<uint32_t>(skeys[i] >> 32);
+        atomicAdd(&hist[(hi - kmin) >> shift], 1u);
+    }
+    G::sync();
+    // thread t owns the `per` bins just below BOUND_BINS - per * t: the top bins come first
+    const int per = BOUND_BINS / nt;                     // 4 (256 threads) or 8 (128 threads)
+    const int top = BOUND_BINS - 1 - per * tid;
+    unsigned int c[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        c[j] = j < per ? hist[top - j] : 0u;
+        sum += c[j];
+    }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = static_cast<int>(incl);
+    G::sync();
+    for (int w = 0; w < warp; w++) incl += static_cast<unsigned int>(s_warp[w]);
+    const unsigned int excl = incl - sum;
+    if (excl < static_cast<unsigned int>(k) && static_cast<unsigned int>(k) <= incl) {
+        unsigned int r = static_cast<unsigned int>(k) - excl;
+        int bin = top;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (r <= c[j]) { bin = top - j; break; }
+            r -= c[j];
+        }
+        *s_prefix = static_cast<unsigned long long>(bin);
+        *s_krem = static_cast<int>(r);
+    }
+    for (int i = tid; i < 256; i += nt) hist[i] = 0;     // (every thread has read its bins)
+    G::sync();
+    const int bin = static_cast<int>(*s_prefix);
+    const int krem = *s_krem;
+    uint32_t bound = kmin + (static_cast<uint32_t>(bin) << shift);
+    if (shift == 0) { G::sync(); return bound; }
+    // split that bin into 256 (or 2^shift) sub-bins
+    const int sub_shift = max(0, shift - 8);
+    for (int i = tid; i < n; i += nt) {
+        const uint32_t off = static_cast<uint32_t>(skeys[i] >> 32) - kmin;
+        if (static_cast<int>(off >> shift) == bin)
+            atomicAdd(&hist[(off - (static_cast<uint32_t>(bin) << shift)) >> sub_shift], 1u);
+    }
+    G::sync();
+    if (tid < 32) {
+        unsigned int d[8], dsum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { d[j] = hist[255 - (8 * lane + j)]; dsum += d[j]; }
+        unsigned int dincl = dsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, dincl, o);
+            if (lane >= o) dincl += t;
+        }
+        const unsigned int dexcl = dincl - dsum;
+        if (dexcl < static_cast<unsigned int>(krem) && static_cast<unsigned int>(krem) <= dincl) {
+            unsigned int r = static_cast<unsigned int>(krem) - dexcl;
+            int digit = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (r <= d[j]) { digit = 255 - (8 * lane + j); break; }
+                r -= d[j];
+            }
+            s_warp[0] = digit;
+        }
+    }
+    G::sync();
+    bound += static_cast<uint32_t>(s_warp[0]) << sub_shift;
+    G::sync();                                           // s_warp is free again
+    return bound;
+}
+
 // In-place stream compaction of keys[0..n): keeps keys whose high word is > hi_thr
 // (or, with by_key, keys >= key_thr).  Returns the number kept (all threads).
 template <class G = CtaGroup>
@@ -497,7 +595,7 @@ __device__ int refresh_list(int q, int k, int cap, unsigned long long* __restric
                             int* s_warp, int scratch_keys = REFRESH_SMEM_KEYS) {
     const int n = cnt[q];
     const int prev = kept[q];
-    if (G::tid() == 0) { s_warp[0] = -1; s_warp[1] = 0; }   // AND / OR of the staged keys' high words
+    if (G::tid() == 0) { s_warp[0] = -1; s_warp[1] = 0; }   // min / max of the staged keys' score words
     G::sync();                                 // everyone has read the counters
     if (n > cap) {
         // more hits than the list holds: this query is re-run on the exact path
@@ -520,35 +618,33 @@ __device__ int refresh_list(int q, int k, int cap, unsigned long long* __restric
     }
     unsigned long long* keys = cand + static_cast<long long>(q) * cap;
     const unsigned long long* src = keys;
-    int first_pass = 0;
-    unsigned long long prefix0 = 0ull;
+    uint32_t ck_word;
     if (n <= scratch_keys) {
-        // the scores of one list lie in a narrow range: the leading byte(s) they all share are
-        // found while the list is staged (AND / OR of the high words) and skipped by the select
-        unsigned int a = 0xFFFFFFFFu, o = 0u;
+        // the list is staged in shared memory once; its smallest / largest score word, found on the
+        // way, span the histogram of the bound select
+        unsigned int lo = 0xFFFFFFFFu, hi = 0u;
         for (int i = G::tid(); i < n; i += G::size()) {
             const unsigned long long key = keys[i];
             scratch[i] = key;
-            a &= static_cast<unsigned int>(key >> 32);
-            o |= static_cast<unsigned int>(key >> 32);
+            lo = min(lo, static_cast<unsigned int>(key >> 32));
+            hi = max(hi, static_cast<unsigned int>(key >> 32));
         }
-        a = __reduce_and_sync(0xffffffffu, a);
-        o = __reduce_or_sync(0xffffffffu, o);
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
         if ((G::tid() & 31) == 0) {
-            atomicAnd(reinterpret_cast<unsigned int*>(&s_warp[0]), a);
-            atomicOr(reinterpret_cast<unsigned int*>(&s_warp[1]), o);
+            atomicMin(reinterpret_cast<unsigned int*>(&s_warp[0]), lo);
+            atomicMax(reinterpret_cast<unsigned int*>(&s_warp[1]), hi);
         }
         G::sync();
         src = scratch;
-        const unsigned int ah = static_cast<unsigned int>(s_warp[0]), oh = static_cast<unsigned int>(s_warp[1]);
-        const int common = (ah == oh) ? 32 : __clz(static_cast<int>(ah ^ oh));
-        first_pass = min(common >> 3, 3);
-        if (first_pass > 0)
-            prefix0 = static_cast<unsigned long long>(ah & (0xFFFFFFFFu << (32 - 8 * first_pass))) << 32;
-        G::sync();                             // s_warp is reused by the compaction below
+        const unsigned int kmin = static_cast<unsigned int>(s_warp[0]), kmax = static_cast<unsigned int>(s_warp[1]);
+        G::sync();                             // s_warp is reused by the select and the compaction
+        ck_word = block_bound_select<G>(scratch, n, k, kmin, kmax, hist, s_prefix, s_krem, s_warp);
+    } else {
+        // lists beyond the staging area (k > 1024): 3-byte radix select out of L2
+        ck_word = static_cast<uint32_t>(block_radix_select<G>(src, n, k, 3, hist, s_prefix, s_krem) >> 32);
     }
-    const unsigned long long pk = block_radix_select<G>(src, n, k, 3, hist, s_prefix, s_krem, first_pass, prefix0);
-    const float ck = unorder_f32(static_cast<uint32_t>(pk >> 32));
+    const float ck = unorder_f32(ck_word);
     float t = __fsub_rd(ck, eps2[q]);
     if (!(t == t)) t = -INFINITY;                    // inf - inf: no usable threshold
     t = nextafterf(t, -INFINITY);                    // admission test is strict
@@ -581,7 +677,7 @@ refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
                          int* __restrict__ cnt, int* __restrict__ kept, float* __restrict__ thr,
                          const float* __restrict__ eps2, int* __restrict__ flags,
                          long long* __restrict__ gstats, const PublishBound pub) {
-    __shared__ unsigned int hist[256];
+    __shared__ unsigned int hist[BOUND_BINS];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_krem;
     __shared__ int s_warp[SEL_THREADS / 32];
@@ -690,7 +786,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) finalize_kernel(const __grid_c
                                                   (p.x32 ? static_cast<size_t>(p.d) * 4 : static_cast<size_t>(p.d_pad) * 2))
                                         : static_cast<size_t>(SORT_CAP) * sizeof(unsigned long long);
     float* sq = reinterpret_cast<float*>(fsm + union_bytes);                             // the query, [d] fp32
-    __shared__ unsigned int hist[256];
+    __shared__ unsigned int hist[BOUND_BINS];     // (the fused refresh's bound select needs all of it)
     __shared__ unsigned long long s_prefix;
     __shared__ int s_krem;
     __shared__ int s_warp[SEL_THREADS / 32];

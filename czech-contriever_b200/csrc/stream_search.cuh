@@ -38,7 +38,7 @@ namespace b2ip {
 constexpr int STREAM_MAX_SLABS = 8;
 constexpr int STREAM_REFRESH_KEYS = 4096;     // list staged in shared memory by the in-kernel refresh (32 KiB: the
                                               // stage count is not what limits the stream -- 5 to 12 stages measure the same)
-constexpr int STREAM_REFRESH_BYTES = STREAM_REFRESH_KEYS * 8 + 256 * 4 /*hist*/ + 64 /*prefix, krem, warp counts*/;
+constexpr int STREAM_REFRESH_BYTES = STREAM_REFRESH_KEYS * 8 + BOUND_BINS * 4 /*hist*/ + 64 /*prefix, krem, warp counts*/;
 constexpr int STREAM_SYNC_WORDS = 2 + 64;     // [0] CTAs arrived at a slab end, [1] abort, [2] queries refreshed;
                                               // (the rest is spare; all zeroed by prep_queries_kernel)
 using EpilogueGroup = WarpRangeGroup<128, 128, 1>;
@@ -104,7 +104,7 @@ coarse_stream_search_kernel(const __grid_constant__ CUtensorMap tmap_q,
     uint8_t* smem_r = smem_q + p.num_k_blocks * Q_KB_BYTES;           // in-kernel refresh
     unsigned long long* r_keys = reinterpret_cast<unsigned long long*>(smem_r);
     unsigned int* r_hist = reinterpret_cast<unsigned int*>(smem_r + STREAM_REFRESH_KEYS * 8);
-    unsigned long long* r_prefix = reinterpret_cast<unsigned long long*>(r_hist + 256);
+    unsigned long long* r_prefix = reinterpret_cast<unsigned long long*>(r_hist + BOUND_BINS);
     int* r_krem = reinterpret_cast<int*>(r_prefix + 1);
     int* r_warp = r_krem + 1;                                         // [8]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + STREAM_REFRESH_BYTES);

@@ -109,7 +109,11 @@ int b2ip_set_stream(b2ip_handle h, void* cuda_stream);
  * "shadow_f16" (B2IP_STORE_F32 only, before the first add): 1 = fp16 operands for the coarse
  * pass instead of bf16 (tighter error bound, saturating at +-65504), "pair" 0/1 CTA-pair kernel,
  * "graph" 0/1 CUDA-graph replay of small-batch searches (env B2IP_GRAPH), "graph_timing" 0/1 keep
- * the per-kernel event records inside the graph (b2ip_stats' coarse_ms etc.). */
+ * the per-kernel event records inside the graph (b2ip_stats' coarse_ms etc.), "stream_kernel" 0/1
+ * streaming kernel for batches <= 64, "stream_stages" cap on its corpus stages in flight per SM,
+ * "stream_fused" 0/1 (env B2IP_STREAM_FUSED, default 0) the whole slab schedule of such a batch in
+ * ONE cooperative launch with in-kernel threshold refreshes (same results; measured slower, see
+ * DESIGN.md 4.1d), "stream_timeout_ms" bound on its in-kernel waits. */
 int b2ip_set_option(b2ip_handle h, const char* name, int64_t value);
 
 /* Optional capacity hint before a series of b2ip_add calls (avoids regrowth copies). */

@@ -95,7 +95,7 @@ def test_small_query_batches_latency_regime(fo, nq, k):
 
 
 @pytest.mark.parametrize("nq,k,d,store", [(1, 10, 768, "f32"), (7, 10, 768, "f32"), (33, 100, 128, "f32"),
-                                          (64, 10, 768, "f32"), (64, 100, 1024, "f32"), (48, 10, 768, "f16"),
+                                          (64, 10, 768, "f32"), (64, 100, 896, "f32"), (48, 10, 768, "f16"),
                                           (64, 1000, 256, "bf16")])
 def test_one_launch_streaming_search_equals_per_slab_launches(fo, nq, k, d, store):
     """Option stream_fused=1: batches of <= 64 queries run the whole slab schedule -- scoring AND the
