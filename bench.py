@@ -76,6 +76,8 @@ def parse(argv=None):
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-search-knn", action="store_true")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: keep equal row shards (default: shards proportional to each GPU's measured scoring rate)")
     ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of each e2e variant (<= --steps)")
     ap.add_argument("--secondary-steps", type=int, default=3)
     # CPU legs (reference arm and the cpu_baseline of the main arm)
@@ -401,6 +403,15 @@ class Dist:
     def sum(self, x):
         return self._red(x, self.dist.ReduceOp.SUM) if self.world > 1 else x
 
+    def all_gather(self, x):
+        """One float per rank, in rank order."""
+        if self.world == 1:
+            return [float(x)]
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
 
 STAT_KEYS = ("coarse_ms", "coarse_flops", "coarse_launches", "launches", "candidates", "rescored", "fallback",
              "slabs", "refresh_ms", "finalize_ms", "device_ms", "max_err_over_eps", "bound_violations")
@@ -590,7 +601,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from b2ip import Engine, ShardedIndex, shard_bounds
+    from b2ip import Engine, ShardedIndex, shard_bounds, weighted_shard_bounds
     from b2ip.indexer import Indexer
 
     rank = int(os.environ.get("RANK", "0"))
@@ -609,11 +620,16 @@ def main():
     D = Dist(torch, dist, world, dev)
 
     N, nq, k, d = args.n_corpus, args.n_queries, args.k, args.d
-    lo, hi = shard_bounds(N, world, rank)
+    weights = None           # per-rank scoring rates (N > 1, see "balance" below); None = equal shards
+
+    def row_shard(n_rows):
+        return weighted_shard_bounds(n_rows, weights, rank) if weights else shard_bounds(n_rows, world, rank)
+
+    lo, hi = row_shard(N)
 
     def build_index(store, n_rows, shadow=None):
         """Row shard [lo,hi) of the first n_rows rows of the synthetic corpus on this rank's GPU."""
-        a, b = shard_bounds(n_rows, world, rank)
+        a, b = row_shard(n_rows)
         ix = ShardedIndex(d, device=local_rank, store=store)
         if shadow is not None:
             ix.engine.set_option("shadow_f16", int(shadow == "f16"))
@@ -628,6 +644,36 @@ def main():
     torch.cuda.synchronize()
     t_ing = time.perf_counter() - t_ing
     q_dev = gen_queries(torch, nq, d, dev)
+
+    # ---------------------------------------------------------------- balance (N > 1)
+    # A row-sharded search ends with its slowest rank, and under the 1 kW cap the B200s of one box
+    # sustain clocks a few percent apart.  Setup, outside every timed region: a few searches on
+    # equal shards measure each rank's scoring rate (FLOP / scoring-kernel time); the shards are
+    # then rebuilt with sizes proportional to those rates (`weighted_shard_bounds`).
+    balance = None
+    if world > 1 and not args.no_balance and args.bound == "tensor":
+        cal_steps = 4
+        for _ in range(2):
+            index.search_owned(q_dev, k)
+        fl = ms = 0.0
+        for _ in range(cal_steps):
+            index.search_owned(q_dev, k)
+            st = index.engine.stats()
+            fl += st["coarse_flops"]
+            ms += st["coarse_ms"]
+        rates = [float(x) for x in D.all_gather(fl / max(ms, 1e-9) / 1e9)]       # TFLOP/s per rank
+        spread = (max(rates) - min(rates)) / max(rates)
+        balance = {"rank_tflops_equal_shards": [round(r, 1) for r in rates], "spread": round(spread, 4),
+                   "applied": bool(spread > 0.005),
+                   "note": "setup, untimed: shard sizes proportional to each GPU's measured scoring rate"}
+        if balance["applied"]:
+            weights = rates
+            index.engine.close()
+            del index
+            torch.cuda.empty_cache()
+            index, lo, hi = build_index(args.store, N, args.shadow)
+            torch.cuda.synchronize()
+        balance["shard_rows"] = [int(x) for x in D.all_gather(float(hi - lo))]
 
     # ---------------------------------------------------------------- device-resident timing
     ms_per_step, agg, last, clocks = timed_device_steps(
@@ -707,7 +753,7 @@ def main():
         q2 = q_dev[:nq2].contiguous()
         ms2, agg2, res2, clocks2 = timed_device_steps(torch, D, ix, q2, k2, steps2, warm2, world,
                                                       sample_clocks_on=local_rank, light=(bound == "hbm"))
-        a, b = shard_bounds(n_rows, world, rank)
+        a, b = row_shard(n_rows)
         pr = parity_probe(torch, dist, D, res2, q2, k2, d, a, b, world, rank, dev,
                           lambda x, y: _probe_rows(x, y, ix))
         secondary[name] = {
@@ -828,7 +874,7 @@ def main():
                 # queries per pipelined chunk (Indexer.knn_chunk): larger chunks cost the GPUs fewer
                 # fixed overheads, smaller ones leave less un-overlapped id mapping at the end
                 sweep = {str(ixr.knn_chunk): best * 1e3}
-                for ch in (32768, 50000):
+                for ch in (16384, 50000):
                     default_chunk, ixr.knn_chunk = ixr.knn_chunk, ch
                     sweep[str(ch)] = time_knn(ixr)[0] * 1e3
                     ixr.knn_chunk = default_chunk
@@ -852,6 +898,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": e2e, "e2e_search_knn": knn, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "parity_probe": probe, "result_checksum": checksum, "secondary": secondary,
+            "balance": balance,
             "detail": {"ingest_s": t_ing, "rows_per_gpu": hi - lo,
                        "candidates_per_query_per_step": agg["candidates"] / args.steps / nq,
                        "rescored_per_query_per_step": agg["rescored"] / args.steps / nq,

@@ -8,5 +8,5 @@ from .engine import Engine, merge_topk  # noqa: F401
 from .faiss_io import read_flat_ip_header, stream_flat_ip_rows, write_flat_ip  # noqa: F401
 from .ingest import index_encoded_data, iter_batches, prefetch  # noqa: F401
 from .multi import MultiGpuEngine, SegmentMap  # noqa: F401
-from .sharded import ShardedIndex, shard_bounds  # noqa: F401
+from .sharded import ShardedIndex, shard_bounds, weighted_shard_bounds  # noqa: F401
 from . import beir_search  # noqa: F401,E402  (BEIR-compatible searcher)

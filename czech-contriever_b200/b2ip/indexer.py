@@ -57,7 +57,7 @@ class Indexer(object):
         self.store = store
         self.index = self._new_engine(vector_sz, "f16" if store == "f16" else "f32")
         self.index_id_to_db_id = []
-        self.knn_chunk = 16384        # queries per pipelined search_knn chunk (env B2IP_KNN_CHUNK)
+        self.knn_chunk = 32768        # queries per pipelined search_knn chunk (env B2IP_KNN_CHUNK)
 
     @classmethod
     def from_engine(cls, engine, ids=None, store=None) -> "Indexer":
@@ -68,7 +68,7 @@ class Indexer(object):
         self.device = getattr(engine, "devices", None) or engine.device
         self.index = engine
         self.index_id_to_db_id = list(ids) if ids is not None else []
-        self.knn_chunk = 16384
+        self.knn_chunk = 32768
         return self
 
     def _new_engine(self, d, store):

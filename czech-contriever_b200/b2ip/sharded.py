@@ -26,6 +26,24 @@ def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(lo + per, n_total)
 
 
+def weighted_shard_bounds(n_total: int, weights, rank: int, align: int = 256) -> Tuple[int, int]:
+    """Contiguous row shard of `rank` when the ranks are not equally fast: shard sizes proportional
+    to `weights` (e.g. each GPU's measured scoring rate -- under the power cap the B200s of one
+    box sustain clocks a few percent apart, and a row-sharded search ends with its slowest
+    rank), boundaries rounded to `align` rows.  Equal weights give `shard_bounds` up to rounding."""
+    w = [max(float(x), 0.0) for x in weights]
+    tot = sum(w)
+    if tot <= 0 or len(w) == 0:
+        return shard_bounds(n_total, max(len(w), 1), rank)
+    edges, acc = [0], 0.0
+    for x in w[:-1]:
+        acc += x
+        e = int(round(n_total * acc / tot / align)) * align
+        edges.append(min(max(e, edges[-1]), n_total))
+    edges.append(n_total)
+    return edges[rank], edges[rank + 1]
+
+
 class ShardedIndex:
     FLAG_BYTES = 256          # per parity: uint32[4 * world] flags (XF_WORDS per rank), padded
 

@@ -113,6 +113,7 @@ struct b2ip_index_s {
     int verbose = 0;
     int pair = 1;                         // CTA-pair (cta_group::2) scoring kernel when nq > 128
     int stream_kernel = 1;                // nq <= 64: streaming kernel (corpus on the MMA's M side)
+    int list_fill_pct = 70;               // adaptive slab schedule: expected list fill after the next slab (% of cap)
     int stream_coop = 1;                  // cooperative launch of that kernel (co-residency guaranteed)
     int stream_stages = 8;                // cap on the corpus stages in flight per SM (tuning)
     int stream_fused = 0;                 // ... with the whole slab schedule + threshold refreshes in ONE launch
@@ -996,7 +997,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             }
             // next slab: expected new hits per query ~ m_max * slab / done; keep the list
             // below ~70 % of its capacity so Poisson noise does not overflow it.
-            const double room = 0.70 * cap - static_cast<double>(m_max);
+            const double room = 0.01 * h->list_fill_pct * cap - static_cast<double>(m_max);
             double next = room > 0 ? static_cast<double>(done) * room / static_cast<double>(m_max)
                                    : static_cast<double>(TILE_X);
             next = std::min(next, 4.0e9);
@@ -1378,6 +1379,7 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "stream_kernel") h->stream_kernel = static_cast<int>(value);
     else if (n == "stream_fused") h->stream_fused = static_cast<int>(value);
     else if (n == "stream_coop") h->stream_coop = static_cast<int>(value);
+    else if (n == "list_fill_pct") h->list_fill_pct = std::min(90, std::max(10, static_cast<int>(value)));
     else if (n == "stream_stages") h->stream_stages = std::max(4, static_cast<int>(value));
     else if (n == "stream_timeout_ms") h->stream_timeout_ns = std::max<int64_t>(1, value) * 1000000ll;
     else if (n == "fuse_refresh") h->fuse_refresh = static_cast<int>(value);

@@ -109,6 +109,23 @@ def test_shard_bounds_partition_rows(built):
             assert max(hi - lo for lo, hi in spans) <= -(-n // g)
 
 
+def test_weighted_shard_bounds_partition_rows(built):
+    """Speed-weighted row shards: a partition of [0, n) in rank order, sizes proportional to the
+    weights up to the alignment, equal weights == equal shards, degenerate weights tolerated."""
+    import b2ip
+    for n in (0, 1, 1000, 21_000_000, 21_015_324):
+        for w in ([1.0], [1, 1], [1.0, 0.97, 1.03, 1.0], [1300, 1340, 1290, 1335, 1310, 1352, 1301, 1322], [0, 0, 5], [0, 0]):
+            g = len(w)
+            spans = [b2ip.weighted_shard_bounds(n, w, r) for r in range(g)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(spans, spans[1:] + [(n, n)]))
+            if sum(w) > 0 and n >= 1_000_000:
+                for (lo, hi), x in zip(spans, w):
+                    assert abs((hi - lo) - n * x / sum(w)) <= 512
+    eq = [b2ip.weighted_shard_bounds(21_000_000, [1.0] * 8, r) for r in range(8)]
+    assert all(abs((hi - lo) - 2_625_000) <= 256 for lo, hi in eq)
+
+
 def test_key_ordering_host_build(tmp_path):
     """keys.cuh compiled for the host: larger key <=> (higher score, then lower row); NaN -> 0."""
     src = tmp_path / "k.cu"

@@ -16,9 +16,10 @@ ap.add_argument("--d", type=int, default=768)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--sweep", default="gx=16")
 ap.add_argument("--verbose", type=int, default=0)
+ap.add_argument("--store", default="f32")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-e = Engine(a.d, 0)
+e = Engine(a.d, 0, store=a.store)
 e.reserve(a.n_corpus)
 CH = 1 << 18
 for c0 in range(0, a.n_corpus, CH):
@@ -39,9 +40,10 @@ for cfg in a.sweep.split(";"):
     for _ in range(a.reps):
         e.search(q, a.k)
         st = e.stats()
-        if best is None or st["coarse_ms"] < best["coarse_ms"]:
+        if best is None or st["total_ms"] < best["total_ms"]:
             best = st
     tf = best["coarse_flops"] / best["coarse_ms"] / 1e9
     print(json.dumps({"cfg": cfg, "coarse_ms": round(best["coarse_ms"], 2), "total_ms": round(best["total_ms"], 2),
+                      "refresh_ms": round(best["refresh_ms"], 2), "finalize_ms": round(best["finalize_ms"], 2),
                       "tflops": round(tf, 1), "cand_per_q": best["candidates"] / a.n_queries,
                       "rescored_per_q": best["rescored"] / a.n_queries, "slabs": best["slabs"]}), flush=True)
