@@ -623,7 +623,18 @@ __device__ int refresh_list(int q, int k, int cap, unsigned long long* __restric
         // the list is staged in shared memory once; its smallest / largest score word, found on the
         // way, span the histogram of the bound select
         unsigned int lo = 0xFFFFFFFFu, hi = 0u;
-        for (int i = G::tid(); i < n; i += G::size()) {
+        int i = G::tid();
+        const int nt = G::size();
+        // four independent loads in flight per thread: this pass is what the kernel waits for
+        for (; i + 3 * nt < n; i += 4 * nt) {
+            const unsigned long long k0 = keys[i], k1 = keys[i + nt], k2 = keys[i + 2 * nt], k3 = keys[i + 3 * nt];
+            scratch[i] = k0; scratch[i + nt] = k1; scratch[i + 2 * nt] = k2; scratch[i + 3 * nt] = k3;
+            const unsigned int h0 = static_cast<unsigned int>(k0 >> 32), h1 = static_cast<unsigned int>(k1 >> 32),
+                               h2 = static_cast<unsigned int>(k2 >> 32), h3 = static_cast<unsigned int>(k3 >> 32);
+            lo = min(min(lo, h0), min(min(h1, h2), h3));
+            hi = max(max(hi, h0), max(max(h1, h2), h3));
+        }
+        for (; i < n; i += nt) {
             const unsigned long long key = keys[i];
             scratch[i] = key;
             lo = min(lo, static_cast<unsigned int>(key >> 32));

@@ -1,2 +1,6 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2ab_bench8.json 2> gpurun_out/r2ab_bench8.err; tail -c 300 gpurun_out/r2ab_bench8.err; python tools/show_bench.py gpurun_out/r2ab_bench8.json; python -c "
-import json; l=json.loads([x for x in open('gpurun_out/r2ab_bench8.json').read().splitlines() if x.startswith('{')][-1]); print(l['balance']); print(l['e2e_search_knn']['ms_per_call_by_chunk'])"
+K='regex:coarse_|finalize_kernel|refresh_threshold|prep_queries|merge_topk|exchange_|shadow_rows|fill_'
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2ac_bench_plain.json 2> gpurun_out/r2ac_bench_plain.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --csv --log-file gpurun_out/r2ac_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2ac_bench_ncu.json 2> gpurun_out/r2ac_bench_ncu.err; wc -l gpurun_out/r2ac_bench_launches.csv
+export B2IP_GRAPH=0
+ncu --set full --import-source on --clock-control none -k regex:refresh_threshold -s 2 -c 1 -f -o gpurun_out/r2ac_refresh_k100_f32 python tools/regimes.py --n-corpus 2625000 --cases 100000:100 --reps 0 > gpurun_out/r2ac_ncu_ref.log 2>&1; tail -1 gpurun_out/r2ac_ncu_ref.log | cut -c1-160
+ls -la gpurun_out/r2ac_*
