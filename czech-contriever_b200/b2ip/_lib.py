@@ -39,7 +39,7 @@ class Stats(ctypes.Structure):
         ("slabs", ctypes.c_int32), ("query_batches", ctypes.c_int32),
         ("refresh_ms", ctypes.c_float), ("finalize_ms", ctypes.c_float),
         ("max_err_over_eps", ctypes.c_double), ("bound_violations", ctypes.c_int64),
-        ("graph_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("graph_mode", ctypes.c_int32), ("sample_rows", ctypes.c_int32),
     ]
 
     def as_dict(self) -> dict:

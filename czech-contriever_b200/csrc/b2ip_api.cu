@@ -101,7 +101,7 @@ struct b2ip_index_s {
     PFN_encodeTiled encode = nullptr;
     // grow-only workspace
     DevBuf q16, eps2, thr, cnt, kept, flags, cand, qstage, qhalf, out_s, out_r, exact_scores, exact_misc,
-        qlist, stage, seg_tab, stream_sync;
+        qlist, stage, seg_tab, stream_sync, gmax;
     int n_seg = 0;                        // row segments (b2ip_set_row_segments); 0 = row_offset
     std::vector<cudaEvent_t> ev_pool, ev_fin;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
@@ -120,6 +120,9 @@ struct b2ip_index_s {
                                           // (stream_search.cuh).  OFF by default: measured, it saves the launch
                                           // structure (-35 us per batch) but streams 3-4 % slower -- see DESIGN 4.1d
     long long stream_timeout_ns = 2ll * 1000000000ll;   // bound on every in-kernel wait of that launch
+    int bootstrap = 1;                    // nq <= 64: threshold from ONE group-max launch over a corpus sample, then
+                                          // one filtered slab over all rows (instead of the geometric slab schedule)
+    int bootstrap_max_mb = 64;            // ... while the sample (read twice) is at most this many MiB of 16-bit rows
     int dense_first = 1;                  // first slab stored positionally (no counters / hit extraction)
     int fuse_refresh = 1;                 // last threshold refresh inside the finalize kernel
     int two_stage = 1;                    // finalize rescoring in two stages (window eps instead of 2 eps)
@@ -149,7 +152,7 @@ struct b2ip_index_s {
         unsigned long long ws_gen, opt_gen;
         bool has_ex; b2ip_exchange_t ex;
         cudaGraphExec_t exec;
-        int coarse_launches, total_launches, slabs;
+        int coarse_launches, total_launches, slabs, sample_rows;
         double coarse_flops;
         size_t ev_used;
         unsigned long long last_use;
@@ -763,6 +766,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             h->stats.coarse_launches = entry->coarse_launches;
             h->stats.total_launches = entry->total_launches;
             h->stats.slabs = entry->slabs;
+            h->stats.sample_rows = entry->sample_rows;
             h->stats.coarse_flops = entry->coarse_flops;
             h->stats.graph_mode = 2;
             ev_used = entry->ev_used;
@@ -835,12 +839,44 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
                 CAP_RC(ensure(h, h->stream_sync, STREAM_SYNC_WORDS * sizeof(unsigned int)));
             }
         }
+        // Threshold bootstrap (latency regime, streaming kernel): the geometric schedule spends two
+        // dependent rounds (dense slab -> refresh -> small slab -> refresh) before the main slab may
+        // start.  Instead: ONE group-max launch over a sample of boot_grid * boot_tw tiles spread
+        // evenly over the corpus (boot_tw tiles per CTA; see coarse_stream_kernel<NQ, true>), the
+        // k-th largest group maximum becomes the threshold, and one filtered slab then covers ALL
+        // rows.  Sample size: the same margin as the geometric schedule -- k * n / sample_rows, the
+        // expected number of rows above the sample's k-th score, is cap / 6: the threshold lies
+        // 2 eps below that score (measured on the benchmark's corpus: x1.5 - x2 more rows at k = 10)
+        // and the k-th order statistic of a sample is noisy (+-32 % at k = 10; a batch of 64 sees
+        // +2.5 sigma).  The sample is read twice, so the bootstrap is only taken when it is a small
+        // part of the corpus (k <= 42 at the default capacity).
+        int boot_grid = 0;
+        int64_t boot_tiles = 0;
+        if (use_stream && !fused_stream && h->bootstrap && !h->dbg && n > slab) {
+            // full tiles only (every group holds a row), the sample at most 1/16 of the corpus, and
+            // >= 16 groups per wanted result (two of the k best rows rarely share a group)
+            const int64_t tiles_all = (n + STREAM_TILE_X - 1) / STREAM_TILE_X;
+            boot_grid = static_cast<int>(std::min<int64_t>(std::min<int64_t>(h->sm_count, BOOT_MAX_GROUPS / STREAM_TILE_X),
+                                                           (tiles_all - 1) / 16));
+            const int64_t want_rows = (6ll * k * n + cap - 1) / cap;
+            boot_tiles = std::max<int64_t>(boot_grid, (want_rows + STREAM_TILE_X - 1) / STREAM_TILE_X);
+            // ... and only while reading the sample twice costs less than the two launch + refresh
+            // rounds it replaces (~45 us): option bootstrap_max_mb (16-bit bytes of the sample).
+            // At d = 768, k = 10 that is a shard of up to ~3M rows -- one GPU of eight on the 21M-row
+            // corpus; a whole-corpus GPU keeps the geometric schedule (measured: DESIGN 4.1e)
+            const int64_t sample_bytes = boot_tiles * STREAM_TILE_X * h->d_pad * 2;
+            if (static_cast<int64_t>(boot_grid) * STREAM_TILE_X < 16ll * k || boot_tiles * 16 > tiles_all - 1 ||
+                sample_bytes > (static_cast<int64_t>(h->bootstrap_max_mb) << 20))
+                boot_grid = 0;
+        }
+        const bool bootstrap = boot_grid > 0;
+        if (bootstrap) CAP_RC(ensure(h, h->gmax, static_cast<size_t>(nq_s) * boot_grid * STREAM_TILE_X * sizeof(uint32_t)));
         prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, h->stream>>>(
             qptr, reinterpret_cast<__nv_bfloat16*>(h->q16.p), nqb, h->d, h->d_pad, h->norm_stats,
             reinterpret_cast<float*>(h->eps2.p), reinterpret_cast<float*>(h->thr.p),
             reinterpret_cast<int*>(h->cnt.p), reinterpret_cast<int*>(h->kept.p),
             reinterpret_cast<int*>(h->flags.p), h->sh, nq_pad, h->gstats,
-            dense_first ? static_cast<int>(first_slab) : 0, dyn,
+            dense_first && !bootstrap ? static_cast<int>(first_slab) : 0, dyn,
             fused_stream ? reinterpret_cast<unsigned int*>(h->stream_sync.p) : nullptr);
         h->stats.total_launches++;
 
@@ -866,13 +902,42 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         // Latency regime (small query batches): a FIXED geometric slab schedule, no host
         // round-trip between slabs.  Growth r is chosen so that ~3k*r expected new hits stay below
         // half the list capacity; a list that overflows anyway sends its query to the exact path.
-        const bool fixed_schedule = nqb <= 2048 && n > slab;
+        const bool fixed_schedule = nqb <= 2048 && n > slab && !bootstrap;
         double growth = 0.0;
         if (fixed_schedule) {
             const double r_max = std::max(2.0, 0.5 * cap / (3.0 * k));
             const double span = static_cast<double>(n) / static_cast<double>(slab);
             const int steps = std::max(1, static_cast<int>(std::ceil(std::log(span) / std::log(r_max))));
             growth = std::pow(span, 1.0 / steps);
+        }
+        if (bootstrap) {
+            const int64_t boot_rows = boot_tiles * STREAM_TILE_X;
+            cp.x_row0 = 0;
+            cp.x_row_end = n;
+            cp.x_tiles = static_cast<int>(boot_tiles);
+            // tile t of the sample = rows [t * gstride, +128): the last one ends before the last full tile does
+            cp.gstride = (n / STREAM_TILE_X) / cp.x_tiles * STREAM_TILE_X;
+            cp.dense = 0;
+            cp.gmax = reinterpret_cast<uint32_t*>(h->gmax.p);
+            cudaEvent_t e0 = get_event(h, ev_used++), e1 = get_event(h, ev_used++), e2 = get_event(h, ev_used++);
+            CAP_TRY(rec(e0));
+            if (nq_s == 32)
+                coarse_stream_kernel<32, true><<<boot_grid, COARSE_THREADS, stream_smem, h->stream>>>(
+                    tmap_q, tmap_x_pair, cp, stream_stages);
+            else
+                coarse_stream_kernel<64, true><<<boot_grid, COARSE_THREADS, stream_smem, h->stream>>>(
+                    tmap_q, tmap_x_pair, cp, stream_stages);
+            CAP_TRY(rec(e1));
+            bootstrap_threshold_kernel<<<nqb, SEL_THREADS, static_cast<size_t>(boot_grid) * STREAM_TILE_X * sizeof(uint32_t), h->stream>>>(
+                reinterpret_cast<const uint32_t*>(h->gmax.p), boot_grid * STREAM_TILE_X, k,
+                reinterpret_cast<float*>(h->thr.p), reinterpret_cast<const float*>(h->eps2.p));
+            CAP_TRY(rec(e2));
+            h->stats.coarse_launches++;
+            h->stats.total_launches += 2;
+            h->stats.slabs++;
+            h->stats.coarse_flops += 2.0 * nqb * static_cast<double>(boot_rows) * h->d;
+            h->stats.sample_rows = static_cast<int32_t>(boot_rows);
+            slab = n;                    // the one filtered slab: every row, the sample included
         }
         while (done < n) {
             int64_t s = std::min<int64_t>(slab, n - done);
@@ -886,7 +951,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             cp.x_row_end = done + s;
             cp.x_tiles = use_stream ? static_cast<int>((s + STREAM_TILE_X - 1) / STREAM_TILE_X)
                                     : static_cast<int>((s + TILE_X - 1) / TILE_X);
-            cp.dense = (done == 0 && dense_first) ? 1 : 0;
+            cp.dense = (done == 0 && dense_first && !bootstrap) ? 1 : 0;
             const bool last = done + s >= n;
             const long long tiles = static_cast<long long>(cp.q_tiles) * cp.x_tiles;
             cudaEvent_t e0 = get_event(h, ev_used++), e1 = get_event(h, ev_used++);
@@ -1093,6 +1158,7 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             ge.exec = exec;
             ge.coarse_launches = h->stats.coarse_launches; ge.total_launches = h->stats.total_launches;
             ge.slabs = h->stats.slabs; ge.coarse_flops = h->stats.coarse_flops;
+            ge.sample_rows = h->stats.sample_rows;
             ge.ev_used = h->graph_timing ? ev_used : 0;
             ge.last_use = ++h->graph_clock;
             h->graphs.push_back(ge);
@@ -1296,6 +1362,9 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
             cudaFuncSetAttribute(coarse_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_stream_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_stream_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
+            cudaFuncSetAttribute(coarse_stream_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
+            cudaFuncSetAttribute(coarse_stream_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
+            cudaFuncSetAttribute(bootstrap_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BOOT_MAX_GROUPS * 4) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_stream_search_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_stream_search_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
             cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
@@ -1325,7 +1394,7 @@ void b2ip_destroy(b2ip_handle h) {
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (DevBuf* b : {&h->q16, &h->eps2, &h->thr, &h->cnt, &h->kept, &h->flags, &h->cand, &h->qstage, &h->qhalf,
                       &h->out_s, &h->out_r, &h->exact_scores, &h->exact_misc, &h->qlist, &h->stage,
-                      &h->seg_tab})
+                      &h->seg_tab, &h->stream_sync, &h->gmax})
         release(*b);
     if (h->v16.base || h->v32.base) {
         vmm_free(h, h->v32);
@@ -1376,6 +1445,8 @@ int b2ip_set_option(b2ip_handle h, const char* name, int64_t value) {
     else if (n == "verbose") h->verbose = static_cast<int>(value);
     else if (n == "pair") h->pair = static_cast<int>(value);
     else if (n == "dense_first") h->dense_first = static_cast<int>(value);
+    else if (n == "bootstrap") h->bootstrap = static_cast<int>(value);
+    else if (n == "bootstrap_max_mb") h->bootstrap_max_mb = static_cast<int>(std::min<int64_t>(std::max<int64_t>(0, value), 1 << 20));
     else if (n == "stream_kernel") h->stream_kernel = static_cast<int>(value);
     else if (n == "stream_fused") h->stream_fused = static_cast<int>(value);
     else if (n == "stream_coop") h->stream_coop = static_cast<int>(value);

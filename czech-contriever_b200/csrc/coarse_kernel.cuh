@@ -64,6 +64,8 @@ struct CoarseParams {
     uint32_t idesc;          // tcgen05 instruction descriptor (IDESC_SINGLE / IDESC_PAIR [format])
     int dbg;                 // perf experiments only (results are wrong when set):
                              // 1 = every tile loads corpus tile 0, 2 = no TMA loads, 4 = no filter
+    uint32_t* gmax;          // coarse_stream_kernel<NQ, true> only: [nq, gridDim.x * 128] group maxima
+    long long gstride;       // ... and the distance in rows between the sampled tiles (>= 128)
 };
 
 __device__ __forceinline__ void tile_coords(const CoarseParams& p, int t, int& qt, int& xt) {
@@ -514,7 +516,16 @@ constexpr int STREAM_ACC = 4;
 constexpr int STREAM_X_STAGE_BYTES = STREAM_TILE_X * KBLOCK_BYTES;   // 16 KiB
 constexpr int STREAM_MISC_BYTES = 1024 /*align*/ + 320 /*barriers*/;
 
-template <int NQ>
+// kGroupMax = the threshold bootstrap of a small batch: one launch over a SAMPLE of x_tiles tiles of
+// 128 rows (x_tiles >= the grid: every CTA sees a tile) spread evenly over the corpus, tile t = rows
+// [t * gstride, +128).  Nothing is filtered or listed; epilogue thread (CTA b, row slot s) keeps,
+// per query, the maximum ordered score over the rows it sees -- row s of tiles b, b + grid, ... ,
+// i.e. a GROUP of rows far apart (neighbouring rows, which score alike in a real corpus, fall
+// into different groups) -- and stores it to gmax[q][b*128 + s].  The groups are
+// disjoint, so the k-th largest group maximum is a lower bound of the k-th best score of the corpus:
+// bootstrap_threshold_kernel turns it into the admission threshold of the ONE filtered slab that
+// follows (instead of dense slab -> refresh -> small slab -> refresh -> main slab).
+template <int NQ, bool kGroupMax = false>
 __global__ void __launch_bounds__(COARSE_THREADS, 1)
 coarse_stream_kernel(const __grid_constant__ CUtensorMap tmap_q,
                      const __grid_constant__ CUtensorMap tmap_x, const CoarseParams p,
@@ -571,7 +582,7 @@ coarse_stream_kernel(const __grid_constant__ CUtensorMap tmap_q,
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const long long x_row = p.x_row0 + static_cast<long long>(t) * STREAM_TILE_X;
+                const long long x_row = p.x_row0 + static_cast<long long>(t) * (kGroupMax ? p.gstride : STREAM_TILE_X);
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_expect_tx(&full_bar[stage], STREAM_X_STAGE_BYTES);
@@ -615,12 +626,45 @@ coarse_stream_kernel(const __grid_constant__ CUtensorMap tmap_q,
     } else if (warp >= 4) {
         // ===================== filter epilogue: thread = corpus row =====================
         const int wq = warp & 3;
+        int as = 0;
+        uint32_t aphase = 0;
+        if constexpr (kGroupMax) {
+            uint32_t gm[NQ];
+#pragma unroll
+            for (int j = 0; j < NQ; j++) gm[j] = 0u;                   // order(NaN): below every score
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const long long row = p.x_row0 + static_cast<long long>(t) * p.gstride + wq * 32 + lane;
+                const bool row_ok = row < p.x_row_end;
+                ptx::mbar_wait(&tfull_bar[as], aphase);
+                ptx::tc_fence_after();
+                const uint32_t taddr =
+                    tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * NQ);
+#pragma unroll
+                for (int c = 0; c < NQ / 32; c++) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const uint32_t o = row_ok ? order_f32(__uint_as_float(v[j])) : 0u;
+                        gm[c * 32 + j] = max(gm[c * 32 + j], o);
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tempty_bar[as]);
+                if (++as == STREAM_ACC) { as = 0; aphase ^= 1; }
+            }
+            // for a fixed query the 128 epilogue threads of a CTA store 128 consecutive words
+            const long long groups = static_cast<long long>(gridDim.x) * STREAM_TILE_X;
+            uint32_t* dst = p.gmax + static_cast<long long>(blockIdx.x) * STREAM_TILE_X + wq * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < NQ; j++)
+                if (j < p.nq) dst[static_cast<long long>(j) * groups] = gm[j];
+        } else {
         float thr_r[NQ];
 #pragma unroll
         for (int j = 0; j < NQ; j++)
             thr_r[j] = j < p.nq ? __ldg(p.thr + j) : __int_as_float(0x7f800000);   // +inf: padding
-        int as = 0;
-        uint32_t aphase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const long long row = p.x_row0 + static_cast<long long>(t) * STREAM_TILE_X + wq * 32 + lane;
             const bool row_ok = row < p.x_row_end;
@@ -665,6 +709,7 @@ coarse_stream_kernel(const __grid_constant__ CUtensorMap tmap_q,
             ptx::mbar_arrive(&tempty_bar[as]);
             if (++as == STREAM_ACC) { as = 0; aphase ^= 1; }
         }
+        }   // !kGroupMax
     }
 
     ptx::tc_fence_before();

@@ -18,6 +18,7 @@ namespace b2ip {
 constexpr int SEL_THREADS = 256;
 constexpr int SORT_CAP = 4096;       // u64 keys sorted in shared memory by finalize
 constexpr int REFRESH_SMEM_KEYS = 4096;   // candidate lists up to this size are refreshed from smem
+constexpr int BOOT_MAX_GROUPS = 160 * 128;   // group maxima per query of the threshold bootstrap (80 KB of smem)
 static_assert(REFRESH_SMEM_KEYS <= SORT_CAP, "finalize stages the fused refresh in its sort buffer");
 constexpr int FLAG_OVERFLOW = 1;
 constexpr int EXACT_QB = 8;          // queries per pass of the exact path
@@ -410,10 +411,15 @@ __device__ unsigned long long block_radix_select(const unsigned long long* __res
 // ulps wide -- and one cheap pass that splits the bin holding the k-th score into 256: the result
 // is within 2^(shift-8) key units (typically 32 ulps, 1e-6 relative) below the true value.
 // hist: BOUND_BINS words.  Ends with a barrier; s_prefix / s_krem / s_warp are free afterwards.
+// K = u64 keys (score word on top) or bare u32 score words; entries whose score word is below kmin
+// are not counted (bootstrap_threshold_kernel: empty groups hold 0), so k counts the others.
 constexpr int BOUND_BINS = 1024;
 
-template <class G = CtaGroup>
-__device__ uint32_t block_bound_select(const unsigned long long* skeys, int n, int k, uint32_t kmin,
+__device__ __forceinline__ uint32_t score_word(unsigned long long key) { return static_cast<uint32_t>(key >> 32); }
+__device__ __forceinline__ uint32_t score_word(uint32_t word) { return word; }
+
+template <class G = CtaGroup, class K = unsigned long long>
+__device__ uint32_t block_bound_select(const K* skeys, int n, int k, uint32_t kmin,
                                        uint32_t kmax, unsigned int* hist,
                                        unsigned long long* s_prefix, int* s_krem, int* s_warp) {
     if (kmin == kmax) return kmin;
@@ -424,8 +430,8 @@ __device__ uint32_t block_bound_select(const unsigned long long* skeys, int n, i
     for (int i = tid; i < BOUND_BINS; i += nt) hist[i] = 0;
     G::sync();
     for (int i = tid; i < n; i += nt) {
-        const uint32_t hi = static_cast<uint32_t>(skeys[i] >> 32);
-        atomicAdd(&hist[(hi - kmin) >> shift], 1u);
+        const uint32_t hi = score_word(skeys[i]);
+        if (hi >= kmin) atomicAdd(&hist[(hi - kmin) >> shift], 1u);
     }
     G::sync();
     // thread t owns the `per` bins just below BOUND_BINS - per * t: the top bins come first
@@ -467,8 +473,9 @@ __device__ uint32_t block_bound_select(const unsigned long long* skeys, int n, i
     // split that bin into 256 (or 2^shift) sub-bins
     const int sub_shift = max(0, shift - 8);
     for (int i = tid; i < n; i += nt) {
-        const uint32_t off = static_cast<uint32_t>(skeys[i] >> 32) - kmin;
-        if (static_cast<int>(off >> shift) == bin)
+        const uint32_t w = score_word(skeys[i]);
+        const uint32_t off = w - kmin;
+        if (w >= kmin && static_cast<int>(off >> shift) == bin)
             atomicAdd(&hist[(off - (static_cast<uint32_t>(bin) << shift)) >> sub_shift], 1u);
     }
     G::sync();
@@ -707,6 +714,126 @@ refresh_threshold_kernel(int k, int cap, unsigned long long* __restrict__ cand,
             if ((pk >> 32) != 0ull) bound = unorder_f32(static_cast<uint32_t>(pk >> 32));   // 0 = a NaN score
         }
         if (threadIdx.x < pub.n_dst) pub.dst[threadIdx.x][q] = bound;
+    }
+}
+
+// Threshold bootstrap of a small batch (tensor_search, latency regime): gmax[q][0..groups) are the
+// group maxima (ordered score words, 0 = empty group / NaN) the streaming kernel's group-max launch
+// wrote; the k-th largest of them is a lower bound of the query's k-th best coarse score (disjoint
+// groups), so thr[q] = that bound - 2 eps_q, exactly what refresh_list derives from a candidate
+// list.  Fewer than k non-empty groups: the threshold stays -inf (every row is admitted, the list
+// overflows and the query is answered by the exact path).  Dynamic shared memory: groups words.
+//
+// k <= BOOT_FAST_K (the latency regime's k = 10): no histogram over 19k words.  Each thread keeps
+// the maximum of the words it stages; the k-th largest of those 256 thread maxima (rank by
+// counting) is itself a lower bound L0 of the k-th largest word -- disjoint subsets again -- and
+// only the handful of words >= L0 can be the k-th largest: they are compacted and ranked exactly.
+constexpr int BOOT_FAST_K = 64;
+
+__global__ void __launch_bounds__(SEL_THREADS)
+bootstrap_threshold_kernel(const uint32_t* __restrict__ gmax, int groups, int k,
+                           float* __restrict__ thr, const float* __restrict__ eps2) {
+    extern __shared__ uint32_t s_gmax[];
+    __shared__ unsigned int hist[BOUND_BINS];          // fast path: thread maxima, then the shortlist
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_krem;
+    __shared__ int s_warp[SEL_THREADS / 32];
+    __shared__ unsigned int s_lo, s_hi, s_valid, s_l0, s_m, s_kth;
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; s_valid = 0u; s_l0 = 0u; s_m = 0u; s_kth = 0u; }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(gmax + static_cast<long long>(q) * groups);   // groups % 128 == 0
+    unsigned int lo = 0xFFFFFFFFu, hi = 0u, valid = 0u;
+    // the staging pass is what this kernel waits for: every load of a thread in flight at once
+    // (BOOT_MAX_GROUPS / 4 / SEL_THREADS = 20 uint4 per thread at most)
+    constexpr int kPerThread = BOOT_MAX_GROUPS / 4 / SEL_THREADS;
+    uint4 v[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; j++) {
+        const int i = tid + j * SEL_THREADS;
+        v[j] = i < groups / 4 ? src[i] : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < kPerThread; j++) {
+        const int i = tid + j * SEL_THREADS;
+        if (i < groups / 4) {
+            reinterpret_cast<uint4*>(s_gmax)[i] = v[j];
+            const unsigned int w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (w[c] != 0u) { lo = min(lo, w[c]); hi = max(hi, w[c]); valid++; }
+        }
+    }
+    const unsigned int my_max = hi;
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if ((tid & 31) == 0) {
+        atomicMin(&s_lo, lo);
+        atomicMax(&s_hi, hi);
+        atomicAdd(&s_valid, valid);
+    }
+    hist[tid] = my_max;
+    __syncthreads();
+    if (static_cast<int>(s_valid) < k) return;               // thr[q] stays -inf (prep_queries_kernel)
+    const unsigned int kmin = s_lo, kmax = s_hi;
+    uint32_t ck_word = 0u;
+    bool have = false;
+    if (k <= BOOT_FAST_K) {
+        // rank of this thread's maximum among the 256 (ties broken by thread index): rank k-1 is L0.
+        // Threads without a word hold 0 and rank last; fewer than k non-empty threads -> L0 = 0,
+        // the shortlist is then every non-empty word (and the histogram path takes over if it is long)
+        int rank = 0;
+        for (int j = 0; j < SEL_THREADS; j++) {
+            const unsigned int o = hist[j];
+            rank += (o > my_max || (o == my_max && j < tid)) ? 1 : 0;
+        }
+        if (rank == k - 1) s_l0 = my_max;
+        __syncthreads();
+        const unsigned int l0 = max(s_l0, 1u);               // 0 = empty group: never listed
+        unsigned int* shortlist = hist + SEL_THREADS;        // BOUND_BINS - SEL_THREADS words
+        for (int i = tid; i < groups / 4; i += SEL_THREADS) {
+            const uint4 v = reinterpret_cast<const uint4*>(s_gmax)[i];
+            const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (w[j] >= l0) {
+                    const unsigned int pos = atomicAdd(&s_m, 1u);
+                    if (pos < static_cast<unsigned int>(BOUND_BINS - SEL_THREADS)) shortlist[pos] = w[j];
+                }
+        }
+        __syncthreads();
+        const int m = static_cast<int>(s_m);
+        if (m >= k && m <= BOUND_BINS - SEL_THREADS) {
+            // exact k-th largest of the shortlist: element i has rank = #(greater) + #(equal before it)
+            for (int i = tid; i < m; i += SEL_THREADS) {
+                const unsigned int mine = shortlist[i];
+                int r = 0;
+                for (int j = 0; j < m; j++) {
+                    const unsigned int o = shortlist[j];
+                    r += (o > mine || (o == mine && j < i)) ? 1 : 0;
+                }
+                if (r == k - 1) s_kth = mine;
+            }
+            __syncthreads();
+            ck_word = s_kth;
+            have = true;
+        }
+        __syncthreads();                                     // hist is reused below
+    }
+    if (!have) {
+        // the group maxima span a wide range (all of [min score, max score], not a candidate list's
+        // narrow top): a second select over [first bound, max] brings the bound within a few ulps
+        ck_word = block_bound_select<CtaGroup, uint32_t>(s_gmax, groups, k, kmin, kmax, hist,
+                                                         &s_prefix, &s_krem, s_warp);
+        ck_word = block_bound_select<CtaGroup, uint32_t>(s_gmax, groups, k, ck_word, kmax, hist,
+                                                         &s_prefix, &s_krem, s_warp);
+    }
+    if (tid == 0) {
+        float t = __fsub_rd(unorder_f32(ck_word), eps2[q]);
+        if (!(t == t)) t = -INFINITY;                        // inf - inf: no usable threshold
+        thr[q] = nextafterf(t, -INFINITY);                   // admission test is strict
     }
 }
 

@@ -86,7 +86,9 @@ typedef struct b2ip_stats_s {
     /* small batches replay their fixed launch sequence from a CUDA graph: 0 = plain launches,
      * 1 = captured by this call, 2 = replayed */
     int32_t graph_mode;
-    int32_t reserved;
+    /* batches of <= 64 queries: rows of the corpus sample whose group maxima gave the first threshold
+     * (one group-max launch + one filtered slab over all rows); 0 = geometric slab schedule */
+    int32_t sample_rows;
 } b2ip_stats_t;
 
 /* replaces faiss.IndexFlatIP(vector_sz)                       -- src/index.py:21

@@ -107,6 +107,7 @@ def test_one_launch_streaming_search_equals_per_slab_launches(fo, nq, k, d, stor
     q = synth(nq, d, 100)
     e = _engine(x, store=store)
     e.set_option("graph", 0)
+    e.set_option("bootstrap", 0)          # the one launch runs the GEOMETRIC schedule: compare like with like
     e.set_option("stream_fused", 1)
     D1, I1 = e.search(q, k)
     s1 = e.stats()
@@ -176,6 +177,102 @@ def test_small_batches_replay_a_cuda_graph(fo):
     e.set_option("graph", 0)
     D0, I0 = e.search(q, 10)
     assert e.stats()["graph_mode"] == 0 and np.array_equal(I0, I) and np.array_equal(D0, D)
+
+
+@pytest.mark.parametrize("nq,k,d,store,n", [(1, 10, 768, "f32", 300_000), (7, 1, 768, "f32", 300_000),
+                                            (33, 40, 128, "f32", 300_000), (64, 10, 768, "f32", 400_000),
+                                            (64, 20, 896, "f32", 150_000), (48, 10, 768, "f16", 300_000),
+                                            (64, 33, 256, "bf16", 300_000), (20, 10, 768, "f32", 9_000)])
+def test_threshold_bootstrap_equals_the_geometric_schedule(fo, nq, k, d, store, n):
+    """Batches of <= 64 queries take their first threshold from ONE group-max launch over a sample
+    of the corpus (coarse_stream_kernel<NQ, true> + bootstrap_threshold_kernel) followed by one
+    filtered slab over all rows, instead of the geometric slab schedule (option bootstrap=0).  The
+    threshold only decides which rows are listed; the answer is the exact top-k either way: bit
+    for bit the same ids and scores, and the oracle's."""
+    x = synth(n, d, 501)
+    # neighbouring rows that score alike (consecutive passages of one article): runs of 24 near-copies
+    # of one row, right where the sample's first tiles lie and elsewhere
+    rng = np.random.default_rng(7)
+    for r0 in (0, 64, 4096, n // 2, n - 4000):
+        x[r0:r0 + 24] = x[r0] + 1e-3 * rng.standard_normal((24, d)).astype(np.float32)
+    q = synth(nq, d, 502)
+    q[0] = x[5]                                       # a query whose best rows ARE such a run
+    e = _engine(x, store=store)
+    e.set_option("graph", 0)
+    Db, Ib = e.search(q, k)
+    sb = e.stats()
+    e.set_option("bootstrap", 0)
+    Dg, Ig = e.search(q, k)
+    sg = e.stats()
+    assert sb["slabs"] == 2 and sb["coarse_launches"] == 2 and sb["sample_rows"] >= 16 * k    # sample + one filtered slab
+    assert sb["sample_rows"] <= n // 16 and sg["sample_rows"] == 0 and sg["slabs"] >= 2
+    assert sb["fallback_queries"] == 0 and sg["fallback_queries"] == 0
+    assert sb["bound_violations"] == 0 and sb["max_err_over_eps"] < 1.0
+    assert np.array_equal(Ib, Ig) and np.array_equal(Db, Dg)
+    # lists stay well inside their capacity
+    assert sb["candidates"] / nq < 0.5 * max(4096, 4 * k)
+    xs = e.export_rows(0, n) if store != "f32" else x
+    Do, Io = fo.search(q, xs, k)
+    fo.compare_topk(Db, Ib, Do, Io, q, xs, rtol=RTOL)
+    # replayed from a CUDA graph, with new queries each time
+    e.set_option("bootstrap", 1)
+    e.set_option("graph", 1)
+    for it in range(3):
+        q2 = synth(nq, d, 600 + it)
+        D2, I2 = e.search(q2, k)
+        assert e.stats()["graph_mode"] == (1 if it == 0 else 2) and e.stats()["sample_rows"] == sb["sample_rows"]
+        Do, Io = fo.search(q2, xs, k)
+        fo.compare_topk(D2, I2, Do, Io, q2, xs, rtol=RTOL)
+
+
+def test_large_k_small_batches_keep_the_geometric_schedule(fo):
+    """The sample would be more than 1/16 of the corpus for k > 42 (at the default list capacity):
+    those batches keep the geometric slab schedule."""
+    x = synth(300_000, 256, 11)
+    q = synth(16, 256, 12)
+    e = _engine(x)
+    for k, boot in ((42, True), (43, False), (100, False), (1000, False)):
+        D, I = e.search(q, k)
+        st = e.stats()
+        assert (st["sample_rows"] > 0) == boot and st["fallback_queries"] == 0, (k, st)
+        Do, Io = fo.search(q, x, k)
+        fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+
+
+def test_threshold_bootstrap_with_unusable_samples(fo):
+    """Degenerate samples -> the search must still be exact (through the exact path if a list
+    overflows): (a) rows in ascending score order; (b) NaN / inf rows inside the sampled tiles;
+    (c) a corpus of copies of one row (every group maximum ties, every row is admitted)."""
+    d, n, k = 256, 200_000, 10
+    base = synth(1, d, 1)[0]
+    # (a) every row a positive multiple of one direction, ascending with the row number
+    x = np.outer(np.linspace(0.1, 1.0, n, dtype=np.float32), base).astype(np.float32)
+    q = np.stack([base, 0.5 * base]).astype(np.float32)
+    e = _engine(x)
+    D, I = e.search(q, k)
+    st = e.stats()
+    Do, Io = fo.search(q, x, k)
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+    assert st["sample_rows"] > 0
+    # (b) non-finite rows in the first tiles (always sampled) and around the corpus
+    x = synth(n, d, 2)
+    x[3, 0] = np.nan
+    x[40, 5] = np.inf
+    x[100_000, 7] = -np.inf
+    x[1000:1010] = 0.0
+    q = synth(9, d, 3)
+    e = _engine(x)
+    D, I = e.search(q, k)
+    Do, Io = fo.search(q, x, k)
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+    # (c) all rows identical: every score ties, faiss keeps the k lowest rows
+    x = np.repeat(synth(1, d, 4), n, axis=0)
+    q = synth(3, d, 5)
+    e = _engine(x)
+    D, I = e.search(q, k)
+    Do, Io = fo.search(q, x, k)
+    fo.compare_topk(D, I, Do, Io, q, x, rtol=RTOL)
+    assert np.array_equal(I, np.tile(np.arange(k), (3, 1)))
 
 
 @pytest.mark.parametrize("nq", [8, 3000])
