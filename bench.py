@@ -587,6 +587,7 @@ def parity_probe(torch, dist, D, res, q_dev, k, d, lo, hi, world, rank, dev, row
 
 
 def main():
+    t_start = time.perf_counter()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
@@ -611,12 +612,14 @@ def main():
         raise SystemExit("bench.py --impl b2ip needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    cpu_group = None
+    cpu_group = guard_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         # a host-only group for the phase where rank 0 alone drives every GPU: an NCCL barrier
         # would leave a spinning kernel on the waiting ranks' GPUs and take SMs from the measurement
         cpu_group = dist.new_group(backend="gloo")
+        import datetime
+        guard_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=180))
     D = Dist(torch, dist, world, dev)
 
     N, nq, k, d = args.n_corpus, args.n_queries, args.k, args.d
@@ -764,6 +767,7 @@ def main():
             "parity_probe": pr, "clocks": clocks2,
             "graph_replay": bool(ix.engine.stats().get("graph_mode", 0) == 2),
             "rescored_per_query": agg2["rescored"] / steps2 / nq2,
+            "threshold_bootstrap_sample_rows": int(ix.engine.stats().get("sample_rows", 0)),
             "fallback_queries": int(agg2["fallback"]),
             "rank0_ms_per_step": {"coarse": agg2["coarse_ms"] / steps2, "refresh": agg2["refresh_ms"] / steps2,
                                   "finalize": agg2["finalize_ms"] / steps2, "search_device_total": agg2["device_ms"] / steps2},
@@ -778,22 +782,49 @@ def main():
                 rows = rows.half().float()
             yield g0, rows
 
+    def guarded(name, fn):
+        # a secondary workload must not cost the primary line: its error is recorded under its name
+        # instead of raised.  N > 1: the searches are collective, so the ranks agree on the outcome
+        # over a host-side group first (a rank that failed ALONE finds nobody there, times out and
+        # the job fails loudly instead of hanging in a half-entered NCCL collective)
+        err = None
+        try:
+            fn()
+        except Exception as e:  # noqa: BLE001
+            err = f"{type(e).__name__}: {e}"[:400]
+        if world > 1:
+            flag = torch.tensor([1 if err else 0], dtype=torch.int32)
+            dist.all_reduce(flag, group=guard_group)
+            if int(flag.item()) and not err:
+                err = "failed on another rank"
+        if err:
+            secondary[name] = {"error": err}
+
     if not args.no_secondary and args.workload == "c3":
         s2 = max(1, args.secondary_steps)
         # C5: latency regime on the same index (batch 64, k = 10), >= 200 batches
-        run_secondary("c5_batch64_k10", index, hi - lo, 64, 10, "hbm", 200, 20, N)
-        run_secondary("c5_batch1_k10", index, hi - lo, 1, 10, "hbm", 200, 20, N)
+        guarded("c5_batch64_k10", lambda: run_secondary("c5_batch64_k10", index, hi - lo, 64, 10, "hbm", 200, 20, N))
+        guarded("c5_batch1_k10", lambda: run_secondary("c5_batch1_k10", index, hi - lo, 1, 10, "hbm", 200, 20, N))
+
         # C2: 1M x 768, 10k queries (a single-GPU config: rank 0's GPU alone at N > 1 would idle
         # the others, so it is sharded like the rest and stays comparable at N = 1)
-        ix2, a2, b2 = build_index("f32", WORKLOADS["c2"]["n_corpus"])
-        run_secondary("c2_1M_10k_k100", ix2, b2 - a2, 10_000, 100, "tensor", 20, 3, WORKLOADS["c2"]["n_corpus"])
-        ix2.engine.close()
-        del ix2
+        def c2():
+            ix2, a2, b2 = build_index("f32", WORKLOADS["c2"]["n_corpus"])
+            try:
+                run_secondary("c2_1M_10k_k100", ix2, b2 - a2, 10_000, 100, "tensor", 20, 3, WORKLOADS["c2"]["n_corpus"])
+            finally:
+                ix2.engine.close()
+
         # C4: bf16-stored corpus, k = 1000
-        ix4, a4, b4 = build_index("bf16", N)
-        run_secondary("c4_bf16_store_k1000", ix4, b4 - a4, nq, 1000, "tensor", s2, 1, N)
-        ix4.engine.close()
-        del ix4
+        def c4():
+            ix4, a4, b4 = build_index("bf16", N)
+            try:
+                run_secondary("c4_bf16_store_k1000", ix4, b4 - a4, nq, 1000, "tensor", s2, 1, N)
+            finally:
+                ix4.engine.close()
+
+        guarded("c2_1M_10k_k100", c2)
+        guarded("c4_bf16_store_k1000", c4)
         torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
@@ -899,6 +930,7 @@ def main():
             "e2e": e2e, "e2e_search_knn": knn, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "parity_probe": probe, "result_checksum": checksum, "secondary": secondary,
             "balance": balance,
+            "wall_s": round(time.perf_counter() - t_start, 1),
             "detail": {"ingest_s": t_ing, "rows_per_gpu": hi - lo,
                        "candidates_per_query_per_step": agg["candidates"] / args.steps / nq,
                        "rescored_per_query_per_step": agg["rescored"] / args.steps / nq,

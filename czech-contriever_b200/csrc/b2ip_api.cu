@@ -1378,6 +1378,8 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
     if (const char* s = getenv("B2IP_GX")) h->gx = std::max(1, atoi(s));
     if (const char* s = getenv("B2IP_STREAM_KERNEL")) h->stream_kernel = atoi(s);
     if (const char* s = getenv("B2IP_STREAM_FUSED")) h->stream_fused = atoi(s);
+    if (const char* s = getenv("B2IP_BOOTSTRAP")) h->bootstrap = atoi(s);
+    if (const char* s = getenv("B2IP_BOOTSTRAP_MAX_MB")) h->bootstrap_max_mb = std::max(0, atoi(s));
     if (const char* s = getenv("B2IP_HINT_Q")) h->hint_q = atoi(s);
     if (const char* s = getenv("B2IP_HINT_X")) h->hint_x = atoi(s);
     if (const char* s = getenv("B2IP_CAND_BUDGET_MB")) h->cand_budget_bytes = std::max(1ll, atoll(s)) << 20;
