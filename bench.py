@@ -685,8 +685,17 @@ def main():
     D_last, I_last, (own_lo, own_hi) = last
     value = nq / (ms_per_step / 1e3)
     roofline = roofline_of(args, D, agg, args.steps, ms_per_step, hi - lo, nq, args.bound, d)
+    def _probe_rows(a, b, ix):
+        # a bf16 / fp16 store is exact w.r.t. the STORED values: the probe sees those ("same inputs")
+        for g0, rows in gen_rows(torch, a, b, d, 1234, dev):
+            if ix.engine.store == "bf16":
+                rows = rows.bfloat16().float()
+            elif ix.engine.store == "f16":
+                rows = rows.half().float()
+            yield g0, rows
+
     probe = parity_probe(torch, dist, D, last, q_dev, k, d, lo, hi, world, rank, dev,
-                         lambda a, b: gen_rows(torch, a, b, d, 1234, dev))
+                         lambda a, b: _probe_rows(a, b, index))
     # order-independent digest of the last step's results, summed over the ranks' query slices:
     # the id sums are identical at every N (the sharded search returns the single-GPU answer),
     # so the scaling runs check each other
@@ -772,15 +781,6 @@ def main():
             "rank0_ms_per_step": {"coarse": agg2["coarse_ms"] / steps2, "refresh": agg2["refresh_ms"] / steps2,
                                   "finalize": agg2["finalize_ms"] / steps2, "search_device_total": agg2["device_ms"] / steps2},
         }
-
-    def _probe_rows(a, b, ix):
-        # a bf16 / fp16 store is exact w.r.t. the STORED values: the probe sees those ("same inputs")
-        for g0, rows in gen_rows(torch, a, b, d, 1234, dev):
-            if ix.engine.store == "bf16":
-                rows = rows.bfloat16().float()
-            elif ix.engine.store == "f16":
-                rows = rows.half().float()
-            yield g0, rows
 
     def guarded(name, fn):
         # a secondary workload must not cost the primary line: its error is recorded under its name

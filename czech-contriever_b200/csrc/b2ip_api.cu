@@ -1123,7 +1123,10 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         cudaEvent_t f0 = get_event(h->ev_fin, 2 * (h->stats.query_batches - 1));
         cudaEvent_t f1 = get_event(h->ev_fin, 2 * (h->stats.query_batches - 1) + 1);
         CAP_TRY(rec(f0));
-        finalize_kernel<true><<<nqb, SEL_THREADS, fin_smem, h->stream>>>(fp);
+        // one instantiation per row storage type: the rescore's inner loop is instruction-issue bound
+        if (fp.x32) finalize_kernel<true, ROWS_F32><<<nqb, SEL_THREADS, fin_smem, h->stream>>>(fp);
+        else if (fp.sh == SH_F16) finalize_kernel<true, ROWS_F16><<<nqb, SEL_THREADS, fin_smem, h->stream>>>(fp);
+        else finalize_kernel<true, ROWS_BF16><<<nqb, SEL_THREADS, fin_smem, h->stream>>>(fp);
         CAP_TRY(rec(f1));
         h->stats.total_launches++;
         // end of the device-side search (re-recorded after the exact fallback, if any): the
@@ -1367,7 +1370,9 @@ int b2ip_create_ex(int d, int device, int store_dtype, b2ip_handle* out) {
             cudaFuncSetAttribute(bootstrap_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BOOT_MAX_GROUPS * 4) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_stream_search_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
             cudaFuncSetAttribute(coarse_stream_search_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_OPTIN) != cudaSuccess ||
-            cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(finalize_kernel<true, ROWS_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(finalize_kernel<true, ROWS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(finalize_kernel<true, ROWS_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
             cudaFuncSetAttribute(finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)) != cudaSuccess ||
             cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(static_cast<size_t>(EXACT_QB) * B2IP_MAX_D * sizeof(float))) != cudaSuccess)

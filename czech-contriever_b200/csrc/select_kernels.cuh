@@ -127,6 +127,12 @@ __device__ __forceinline__ float2 unpack2_sh(uint32_t raw, int sh) {
     if (sh == SH_F16) return __half22float2(*reinterpret_cast<const __half2*>(&raw));
     return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
 }
+// the same with the element type known at compile time; bf16 -> fp32 is a shift / a mask per element
+template <int kSh>
+__device__ __forceinline__ float2 unpack2_t(uint32_t raw) {
+    if constexpr (kSh == SH_F16) return __half22float2(*reinterpret_cast<const __half2*>(&raw));
+    else return make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xFFFF0000u));
+}
 
 // ---------------------------------------------------------------------------------------
 // corpus ingest
@@ -907,7 +913,12 @@ __device__ void block_bitonic_desc(unsigned long long* s, int P) {
     }
 }
 
-template <bool kRescore>
+// kRows = how the rows the rescore reads are stored: ROWS_F32 (fp32 master rows, p.x32) or
+// ROWS_BF16 / ROWS_F16 (a 16-bit store, p.x16) -- a compile-time constant, so the inner loop of the
+// rescore (instruction-issue bound) carries one unpack sequence instead of both under predicates.
+enum { ROWS_F32 = 0, ROWS_BF16 = 1, ROWS_F16 = 2 };
+
+template <bool kRescore, int kRows = ROWS_F32>
 __global__ void __launch_bounds__(SEL_THREADS, 3) finalize_kernel(const __grid_constant__ FinalizeParams p) {
     // graph replay: the per-call values come from DynArgs (the parameter block itself stays in
     // constant memory: no local copy)
@@ -921,7 +932,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) finalize_kernel(const __grid_c
     // (the ring is live only inside rescore_range, the sort buffer only outside of it)
     const size_t union_bytes = kRescore ? max(static_cast<size_t>(SORT_CAP) * sizeof(unsigned long long),
                                               static_cast<size_t>(blockDim.x >> 5) * p.ring_stages *
-                                                  (p.x32 ? static_cast<size_t>(p.d) * 4 : static_cast<size_t>(p.d_pad) * 2))
+                                                  (kRows == ROWS_F32 ? static_cast<size_t>(p.d) * 4 : static_cast<size_t>(p.d_pad) * 2))
                                         : static_cast<size_t>(SORT_CAP) * sizeof(unsigned long long);
     float* sq = reinterpret_cast<float*>(fsm + union_bytes);                             // the query, [d] fp32
     __shared__ unsigned int hist[BOUND_BINS];     // (the fused refresh's bound select needs all of it)
@@ -998,7 +1009,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) finalize_kernel(const __grid_c
             t = fmaf(a.z, b.z, t);
             return fmaf(a.w, b.w, t);
         };
-        const bool rows16 = p.x32 == nullptr;
+        constexpr bool rows16 = kRows != ROWS_F32;
+        constexpr int kSh = kRows == ROWS_F16 ? SH_F16 : SH_BF16;
         const int chunk_elems = rows16 ? 8 : 4;                    // elements per 16-byte chunk of a stored row
         const int row_bytes = rows16 ? p.d_pad * 2 : p.d * 4;
         const int n_chunks = row_bytes >> 4;
@@ -1034,8 +1046,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) finalize_kernel(const __grid_c
                         const int c = lane + 32 * u;
                         if (c < n_chunks) {
                             const uint4 v = srow[c];
-                            const float2 e0 = unpack2_sh(v.x, p.sh), e1 = unpack2_sh(v.y, p.sh);
-                            const float2 e2 = unpack2_sh(v.z, p.sh), e3 = unpack2_sh(v.w, p.sh);
+                            const float2 e0 = unpack2_t<kSh>(v.x), e1 = unpack2_t<kSh>(v.y);
+                            const float2 e2 = unpack2_t<kSh>(v.z), e3 = unpack2_t<kSh>(v.w);
                             acc += static_cast<double>(dot4(make_float4(e0.x, e0.y, e1.x, e1.y), qreg[2 * u]));
                             acc += static_cast<double>(dot4(make_float4(e2.x, e2.y, e3.x, e3.y), qreg[2 * u + 1]));
                         }
@@ -1049,8 +1061,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) finalize_kernel(const __grid_c
                         acc += static_cast<double>(dot4(make_float4(__uint_as_float(v.x), __uint_as_float(v.y),
                                                                     __uint_as_float(v.z), __uint_as_float(v.w)), q4[c]));
                     } else {
-                        const float2 e0 = unpack2_sh(v.x, p.sh), e1 = unpack2_sh(v.y, p.sh);
-                        const float2 e2 = unpack2_sh(v.z, p.sh), e3 = unpack2_sh(v.w, p.sh);
+                        const float2 e0 = unpack2_t<kSh>(v.x), e1 = unpack2_t<kSh>(v.y);
+                        const float2 e2 = unpack2_t<kSh>(v.z), e3 = unpack2_t<kSh>(v.w);
                         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                         const float4 qa = (8 * c < p.d) ? q4[2 * c] : z, qb = (8 * c + 4 < p.d) ? q4[2 * c + 1] : z;
                         acc += static_cast<double>(dot4(make_float4(e0.x, e0.y, e1.x, e1.y), qa));
