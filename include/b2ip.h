@@ -115,7 +115,11 @@ int b2ip_set_stream(b2ip_handle h, void* cuda_stream);
  * streaming kernel for batches <= 64, "stream_stages" cap on its corpus stages in flight per SM,
  * "stream_fused" 0/1 (env B2IP_STREAM_FUSED, default 0) the whole slab schedule of such a batch in
  * ONE cooperative launch with in-kernel threshold refreshes (same results; measured slower, see
- * DESIGN.md 4.1d), "stream_timeout_ms" bound on its in-kernel waits. */
+ * DESIGN.md 4.1d), "stream_timeout_ms" bound on its in-kernel waits, "bootstrap" 0/1 (env
+ * B2IP_BOOTSTRAP, default 1) first threshold of a batch <= 64 from the group maxima of a corpus
+ * sample + ONE filtered slab over all rows instead of the geometric slab schedule, taken while the
+ * sample is at most "bootstrap_max_mb" (env B2IP_BOOTSTRAP_MAX_MB, default 64) MiB of 16-bit rows
+ * (same results; b2ip_stats_t.sample_rows tells which schedule ran). */
 int b2ip_set_option(b2ip_handle h, const char* name, int64_t value);
 
 /* Optional capacity hint before a series of b2ip_add calls (avoids regrowth copies). */
