@@ -31,7 +31,7 @@ for line in sass.splitlines():
                     counts[cur]["UTCHMMA.2CTA"] += 1
                 if p == "UTMALDG" and ".2CTA" in op:
                     counts[cur]["UTMALDG.2CTA"] += 1
-print("# SASS opcode summary of libb2ip.so (round 2)\n")
+print("# SASS opcode summary of libb2ip.so (final code of round 2)\n")
 print(f"`cuobjdump -sass czech-contriever_b200/lib/libb2ip.so`, architectures in the file: {sorted(set(arch))}.")
 print("UTCHMMA = tcgen05.mma kind::f16, LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor (TMA), UTCBAR = tcgen05.commit,")
 print("SYNCS = mbarrier ops, HMMA = legacy mma.sync (must be 0).\n")
