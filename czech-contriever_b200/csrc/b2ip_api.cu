@@ -860,6 +860,9 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
                                                            (tiles_all - 1) / 16));
             const int64_t want_rows = (6ll * k * n + cap - 1) / cap;
             boot_tiles = std::max<int64_t>(boot_grid, (want_rows + STREAM_TILE_X - 1) / STREAM_TILE_X);
+            // the launch lasts as long as its busiest CTA: a few tiles past a whole wave are not worth
+            // another round (2,625,000 rows: 301 tiles -> 296 = 2 per SM; the sample shrinks by < 1/8 wave)
+            if (boot_tiles > boot_grid && boot_tiles % boot_grid < boot_grid / 8) boot_tiles -= boot_tiles % boot_grid;
             // ... and only while reading the sample twice costs less than the two launch + refresh
             // rounds it replaces (~45 us): option bootstrap_max_mb (16-bit bytes of the sample).
             // At d = 768, k = 10 that is a shard of up to ~3M rows -- one GPU of eight on the 21M-row

@@ -740,17 +740,15 @@ __global__ void __launch_bounds__(SEL_THREADS)
 bootstrap_threshold_kernel(const uint32_t* __restrict__ gmax, int groups, int k,
                            float* __restrict__ thr, const float* __restrict__ eps2) {
     extern __shared__ uint32_t s_gmax[];
-    __shared__ unsigned int hist[BOUND_BINS];          // fast path: thread maxima, then the shortlist
+    __shared__ __align__(16) unsigned int hist[BOUND_BINS];   // fast path: thread maxima, then the shortlist
     __shared__ unsigned long long s_prefix;
     __shared__ int s_krem;
     __shared__ int s_warp[SEL_THREADS / 32];
     __shared__ unsigned int s_lo, s_hi, s_valid, s_l0, s_m, s_kth;
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    if (tid == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; s_valid = 0u; s_l0 = 0u; s_m = 0u; s_kth = 0u; }
-    __syncthreads();
+    if (tid == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; s_valid = 0u; s_l0 = 0xFFFFFFFFu; s_m = 0u; s_kth = 0u; }
     const uint4* src = reinterpret_cast<const uint4*>(gmax + static_cast<long long>(q) * groups);   // groups % 128 == 0
-    unsigned int lo = 0xFFFFFFFFu, hi = 0u, valid = 0u;
     // the staging pass is what this kernel waits for: every load of a thread in flight at once
     // (BOOT_MAX_GROUPS / 4 / SEL_THREADS = 20 uint4 per thread at most)
     constexpr int kPerThread = BOOT_MAX_GROUPS / 4 / SEL_THREADS;
@@ -758,79 +756,89 @@ bootstrap_threshold_kernel(const uint32_t* __restrict__ gmax, int groups, int k,
 #pragma unroll
     for (int j = 0; j < kPerThread; j++) {
         const int i = tid + j * SEL_THREADS;
-        v[j] = i < groups / 4 ? src[i] : make_uint4(0u, 0u, 0u, 0u);
+        v[j] = src[min(i, groups / 4 - 1)];       // unpredicated (7 predicate registers would cap the loads in flight)
     }
+    unsigned int my_max = 0u;
 #pragma unroll
     for (int j = 0; j < kPerThread; j++) {
         const int i = tid + j * SEL_THREADS;
         if (i < groups / 4) {
             reinterpret_cast<uint4*>(s_gmax)[i] = v[j];
-            const unsigned int w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (w[c] != 0u) { lo = min(lo, w[c]); hi = max(hi, w[c]); valid++; }
+            my_max = max(max(my_max, max(v[j].x, v[j].y)), max(v[j].z, v[j].w));
         }
-    }
-    const unsigned int my_max = hi;
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    valid = __reduce_add_sync(0xffffffffu, valid);
-    if ((tid & 31) == 0) {
-        atomicMin(&s_lo, lo);
-        atomicMax(&s_hi, hi);
-        atomicAdd(&s_valid, valid);
     }
     hist[tid] = my_max;
     __syncthreads();
-    if (static_cast<int>(s_valid) < k) return;               // thr[q] stays -inf (prep_queries_kernel)
-    const unsigned int kmin = s_lo, kmax = s_hi;
     uint32_t ck_word = 0u;
     bool have = false;
     if (k <= BOOT_FAST_K) {
-        // rank of this thread's maximum among the 256 (ties broken by thread index): rank k-1 is L0.
-        // Threads without a word hold 0 and rank last; fewer than k non-empty threads -> L0 = 0,
-        // the shortlist is then every non-empty word (and the histogram path takes over if it is long)
-        int rank = 0;
-        for (int j = 0; j < SEL_THREADS; j++) {
-            const unsigned int o = hist[j];
-            rank += (o > my_max || (o == my_max && j < tid)) ? 1 : 0;
+        // r = how many thread maxima are strictly greater than mine.  The k-th largest of the 256
+        // is the smallest one with r <= k - 1 (ties share their r): L0.  Threads without a word hold
+        // 0; fewer than k non-empty threads -> L0 = 0 and the general path below takes over.
+        int r = 0;
+        const uint4* h4 = reinterpret_cast<const uint4*>(hist);
+#pragma unroll 4
+        for (int j = 0; j < SEL_THREADS / 4; j++) {
+            const uint4 o = h4[j];
+            r += (o.x > my_max ? 1 : 0) + (o.y > my_max ? 1 : 0) + (o.z > my_max ? 1 : 0) + (o.w > my_max ? 1 : 0);
         }
-        if (rank == k - 1) s_l0 = my_max;
+        if (r <= k - 1) atomicMin(&s_l0, my_max);
         __syncthreads();
-        const unsigned int l0 = max(s_l0, 1u);               // 0 = empty group: never listed
-        unsigned int* shortlist = hist + SEL_THREADS;        // BOUND_BINS - SEL_THREADS words
-        for (int i = tid; i < groups / 4; i += SEL_THREADS) {
-            const uint4 v = reinterpret_cast<const uint4*>(s_gmax)[i];
-            const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+        const unsigned int l0 = s_l0;
+        if (l0 != 0u) {
+            unsigned int* shortlist = hist + SEL_THREADS;        // BOUND_BINS - SEL_THREADS words
+            for (int i = tid; i < groups / 4; i += SEL_THREADS) {
+                const uint4 w4 = reinterpret_cast<const uint4*>(s_gmax)[i];
+                const unsigned int w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (w[j] >= l0) {
-                    const unsigned int pos = atomicAdd(&s_m, 1u);
-                    if (pos < static_cast<unsigned int>(BOUND_BINS - SEL_THREADS)) shortlist[pos] = w[j];
-                }
-        }
-        __syncthreads();
-        const int m = static_cast<int>(s_m);
-        if (m >= k && m <= BOUND_BINS - SEL_THREADS) {
-            // exact k-th largest of the shortlist: element i has rank = #(greater) + #(equal before it)
-            for (int i = tid; i < m; i += SEL_THREADS) {
-                const unsigned int mine = shortlist[i];
-                int r = 0;
-                for (int j = 0; j < m; j++) {
-                    const unsigned int o = shortlist[j];
-                    r += (o > mine || (o == mine && j < i)) ? 1 : 0;
-                }
-                if (r == k - 1) s_kth = mine;
+                for (int j = 0; j < 4; j++)
+                    if (w[j] >= l0) {
+                        const unsigned int pos = atomicAdd(&s_m, 1u);
+                        if (pos < static_cast<unsigned int>(BOUND_BINS - SEL_THREADS)) shortlist[pos] = w[j];
+                    }
             }
             __syncthreads();
-            ck_word = s_kth;
-            have = true;
+            const int m = static_cast<int>(s_m);                 // >= k: k thread maxima are >= L0
+            if (m <= BOUND_BINS - SEL_THREADS) {
+                // exact k-th largest of the shortlist: element i has rank = #(greater) + #(equal before it)
+                for (int i = tid; i < m; i += SEL_THREADS) {
+                    const unsigned int mine = shortlist[i];
+                    int rk = 0;
+                    for (int j = 0; j < m; j++) {
+                        const unsigned int o = shortlist[j];
+                        rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
+                    }
+                    if (rk == k - 1) s_kth = mine;
+                }
+                __syncthreads();
+                ck_word = s_kth;
+                have = true;
+            }
         }
         __syncthreads();                                     // hist is reused below
     }
     if (!have) {
-        // the group maxima span a wide range (all of [min score, max score], not a candidate list's
-        // narrow top): a second select over [first bound, max] brings the bound within a few ulps
+        // general path (k > BOOT_FAST_K, empty groups / NaN scores, thousands of ties): smallest /
+        // largest non-empty word and their count, then the histogram bound select.  The group maxima
+        // span a wide range (all of [min score, max score], not a candidate list's narrow top): a
+        // second select over [first bound, max] brings the bound within a few ulps of the k-th
+        unsigned int lo = 0xFFFFFFFFu, hi = 0u, valid = 0u;
+        for (int i = tid; i < groups; i += SEL_THREADS) {
+            const unsigned int w = s_gmax[i];
+            if (w != 0u) { lo = min(lo, w); hi = max(hi, w); valid++; }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        valid = __reduce_add_sync(0xffffffffu, valid);
+        if ((tid & 31) == 0) {
+            atomicMin(&s_lo, lo);
+            atomicMax(&s_hi, hi);
+            atomicAdd(&s_valid, valid);
+        }
+        __syncthreads();
+        if (static_cast<int>(s_valid) < k) return;           // thr[q] stays -inf (prep_queries_kernel)
+        const unsigned int kmin = s_lo, kmax = s_hi;
+        __syncthreads();
         ck_word = block_bound_select<CtaGroup, uint32_t>(s_gmax, groups, k, kmin, kmax, hist,
                                                          &s_prefix, &s_krem, s_warp);
         ck_word = block_bound_select<CtaGroup, uint32_t>(s_gmax, groups, k, ck_word, kmax, hist,

@@ -127,6 +127,44 @@ def test_c5_small_batches_on_the_full_corpus(full_index):
             _assert_matches_fp64(torch, Ds, Is, best_s[:b], best_i[:b], f"C5 batch {b}")
 
 
+def test_c5_small_batches_on_one_shard_of_eight():
+    """Config 5 as ONE GPU of eight sees it: rows [0, 2,625,000) of the benchmark's corpus, batches
+    of 1-64, k = 10.  At this size the first threshold comes from the group maxima of a corpus
+    sample (`sample_rows` > 0) instead of the geometric slab schedule -- checked
+    against the fp64 brute force over the shard, and bit for bit against that schedule."""
+    import torch
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from bench import gen_rows
+    from b2ip import Engine
+    dev = torch.device("cuda", 0)
+    n = N // 8
+    e = Engine(D, 0)
+    e.reserve(n)
+    for _, rows in gen_rows(torch, 0, n, D, 1234, dev):
+        e.add(rows)
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    q = torch.randn((64, D), generator=gen, device=dev)
+    q /= q.norm(dim=1, keepdim=True)
+    best_s, best_i = _fp64_topk(torch, q.double(), gen_rows(torch, 0, n, D, 1234, dev), 10, dev)
+    for b in (1, 7, 33, 64):
+        qb = q[:b].contiguous()
+        for rep in range(2):                       # second call replays the CUDA graph
+            Ds, Is = e.search(qb, 10)
+            st = e.stats()
+            assert st["sample_rows"] > 0 and st["slabs"] == 2, st
+            assert st["fallback_queries"] == 0 and st["bound_violations"] == 0 and st["max_err_over_eps"] < 1.0
+            assert st["graph_mode"] == (1 if rep == 0 else 2)
+            assert st["candidates"] / b < 2048, st        # lists at most half full
+            _assert_matches_fp64(torch, Ds, Is, best_s[:b], best_i[:b], f"C5 shard batch {b}")
+        e.set_option("bootstrap", 0)
+        Dg, Ig = e.search(qb, 10)
+        assert e.stats()["sample_rows"] == 0
+        assert torch.equal(Ig, Is) and torch.equal(Dg, Ds)
+        e.set_option("bootstrap", 1)
+    e.close()
+
+
 def test_c4_bf16_store_k1000_on_the_full_corpus(full_index):
     """Config 4 at full size: 21M bf16-STORED rows, k = 1000.  The index is exact w.r.t. the
     stored (bf16-rounded) values, so the fp64 truth is computed from those ("same inputs")."""

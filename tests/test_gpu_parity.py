@@ -226,12 +226,13 @@ def test_threshold_bootstrap_equals_the_geometric_schedule(fo, nq, k, d, store, 
 
 
 def test_large_k_small_batches_keep_the_geometric_schedule(fo):
-    """The sample would be more than 1/16 of the corpus for k > 42 (at the default list capacity):
-    those batches keep the geometric slab schedule."""
+    """The sample would be more than 1/16 of the corpus for k > ~42 (at the default list capacity;
+    the limit is soft: a sample a few tiles past a whole wave is cut to the wave): those batches
+    keep the geometric slab schedule."""
     x = synth(300_000, 256, 11)
     q = synth(16, 256, 12)
     e = _engine(x)
-    for k, boot in ((42, True), (43, False), (100, False), (1000, False)):
+    for k, boot in ((42, True), (60, False), (100, False), (1000, False)):
         D, I = e.search(q, k)
         st = e.stats()
         assert (st["sample_rows"] > 0) == boot and st["fallback_queries"] == 0, (k, st)

@@ -1,6 +1,7 @@
 """Condenses ncu outputs into the small tracked files under profiles/.
     python tools/ncu_summary.py launches <launches.csv>            -> per-kernel time shares
-    python tools/ncu_summary.py full <report.ncu-rep> [n_top]      -> key metrics + hottest SASS lines
+    python tools/ncu_summary.py full <report.ncu-rep> [n_top] [kernel_regex]  -> key metrics + hottest SASS lines
+                                                   (of the first captured launch whose name matches kernel_regex)
 """
 import collections, csv, io, re, subprocess, sys
 
@@ -20,8 +21,9 @@ def launches(path):
     print(f"| total | | {tot:.2f} | |")
 
 
-def full(rep, n_top=12):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def full(rep, n_top=12, kernel=None):
+    sel = ["--kernel-name", "regex:" + kernel, "--launch-count", "1"] if kernel else []
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
@@ -37,10 +39,10 @@ def full(rep, n_top=12):
     for k in keys:
         if k in d:
             print(f"| {k} | {d[k][1]} | {d[k][0]} |")
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
     hdr = rows[1]; ci = {h: i for i, h in enumerate(hdr)}
-    data = rows[2:]
+    data = [r for r in rows[2:] if len(r) == len(hdr)]
     stall = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(float(r[ci["# Samples"]] or 0) for r in data)
     print(f"\nHottest SASS lines (of {tot:.0f} warp samples):\n\n| samples | share | executed | SASS | top stall |\n|---:|---:|---:|---|---|")
@@ -50,9 +52,10 @@ def full(rep, n_top=12):
         print(f"| {s:.0f} | {100 * s / tot:.1f}% | {float(r[ci['Instructions Executed']]):.0f} | `{r[ci['Source']].strip()[:70]}` | {top[1]} |")
 
 
-def lines(rep, n_top=25):
+def lines(rep, n_top=25, kernel=None):
     """Warp-stall samples per CUDA source line (needs -lineinfo): where a kernel spends its time."""
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+    sel = ["--kernel-name", "regex:" + kernel, "--launch-count", "1"] if kernel else []
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + sel,
                          capture_output=True, text=True).stdout
     fname, out = None, []
     for row in csv.reader(io.StringIO(src)):
@@ -74,6 +77,6 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
     elif sys.argv[1] == "lines":
-        lines(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 25)
+        lines(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 25, sys.argv[4] if len(sys.argv) > 4 else None)
     else:
-        full(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 12)
+        full(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 12, sys.argv[4] if len(sys.argv) > 4 else None)
