@@ -841,8 +841,8 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         }
         // Threshold bootstrap (latency regime, streaming kernel): the geometric schedule spends two
         // dependent rounds (dense slab -> refresh -> small slab -> refresh) before the main slab may
-        // start.  Instead: ONE group-max launch over a sample of boot_grid * boot_tw tiles spread
-        // evenly over the corpus (boot_tw tiles per CTA; see coarse_stream_kernel<NQ, true>), the
+        // start.  Instead: ONE group-max launch over a sample of boot_tiles tiles spread evenly
+        // over the corpus (boot_grid CTAs; see coarse_stream_kernel<NQ, true>), the
         // k-th largest group maximum becomes the threshold, and one filtered slab then covers ALL
         // rows.  Sample size: the same margin as the geometric schedule -- k * n / sample_rows, the
         // expected number of rows above the sample's k-th score, is cap / 6: the threshold lies
@@ -862,7 +862,8 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
             boot_tiles = std::max<int64_t>(boot_grid, (want_rows + STREAM_TILE_X - 1) / STREAM_TILE_X);
             // the launch lasts as long as its busiest CTA: a few tiles past a whole wave are not worth
             // another round (2,625,000 rows: 301 tiles -> 296 = 2 per SM; the sample shrinks by < 1/8 wave)
-            if (boot_tiles > boot_grid && boot_tiles % boot_grid < boot_grid / 8) boot_tiles -= boot_tiles % boot_grid;
+            if (boot_grid > 0 && boot_tiles > boot_grid && boot_tiles % boot_grid < boot_grid / 8)
+                boot_tiles -= boot_tiles % boot_grid;
             // ... and only while reading the sample twice costs less than the two launch + refresh
             // rounds it replaces (~45 us): option bootstrap_max_mb (16-bit bytes of the sample).
             // At d = 768, k = 10 that is a shard of up to ~3M rows -- one GPU of eight on the 21M-row
