@@ -23,7 +23,7 @@ SYMBOLS = (
     "b2ip_create", "b2ip_create_ex", "b2ip_destroy", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_ntotal",
     "b2ip_dim", "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_ex", "b2ip_search_exchange", "b2ip_enable_peer_access", "b2ip_group_create", "b2ip_group_destroy", "b2ip_group_search", "b2ip_group_last_error",
     "b2ip_merge_topk", "b2ip_merge_topk_strided", "b2ip_export_rows",
-    "b2ip_copy_to_device", "b2ip_copy_to_host", "b2ip_stats", "b2ip_last_error", "b2ip_debug_coarse_scores", "b2ip_version",
+    "b2ip_copy_to_device", "b2ip_copy_to_host", "b2ip_stats", "b2ip_last_error", "b2ip_debug_coarse_scores", "b2ip_debug_plan_bootstrap", "b2ip_version",
 )
 
 
@@ -115,6 +115,9 @@ def load() -> ctypes.CDLL:
     lib.b2ip_last_error.argtypes = [vp]
     lib.b2ip_last_error.restype = ctypes.c_char_p
     lib.b2ip_debug_coarse_scores.argtypes = [vp, i64, vp, i64, i64, vp]
+    lib.b2ip_debug_plan_bootstrap.argtypes = [i64, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int32),
+                                              ctypes.POINTER(ctypes.c_int64)]
+    lib.b2ip_debug_plan_bootstrap.restype = i32
     lib.b2ip_version.restype = ctypes.c_char_p
     for name in ("b2ip_create", "b2ip_create_ex", "b2ip_set_stream", "b2ip_set_option", "b2ip_reserve", "b2ip_add", "b2ip_dim",
                  "b2ip_set_row_offset", "b2ip_set_row_segments", "b2ip_search", "b2ip_search_ex", "b2ip_search_exchange", "b2ip_enable_peer_access", "b2ip_merge_topk", "b2ip_merge_topk_strided",

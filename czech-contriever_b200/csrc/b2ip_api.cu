@@ -661,6 +661,34 @@ int enqueue_exchange(b2ip_handle h, int64_t nq, int k, const DynArgs* dyn = null
 }
 
 // ------------------------------------------------------------------------- tensor path
+// Sample of the threshold bootstrap (see tensor_search): *grid CTAs over *tiles tiles of 128 rows, or
+// *grid = 0 when the batch keeps the geometric schedule.  Pure host arithmetic (also reachable as
+// b2ip_debug_plan_bootstrap, so the CPU test suite can sweep it without a GPU).
+void plan_bootstrap(int64_t n, int k, int cap, int sm_count, int d_pad, int max_mb, int* grid, int64_t* tiles) {
+    *grid = 0;
+    *tiles = 0;
+    if (n <= 0 || k < 1 || cap < 1 || sm_count < 1) return;
+    // full tiles only (every group holds a row), the sample at most 1/16 of the corpus, and
+    // >= 16 groups per wanted result (two of the k best rows rarely share a group)
+    const int64_t tiles_all = (n + STREAM_TILE_X - 1) / STREAM_TILE_X;
+    const int boot_grid = static_cast<int>(std::min<int64_t>(std::min<int64_t>(sm_count, BOOT_MAX_GROUPS / STREAM_TILE_X),
+                                                             (tiles_all - 1) / 16));
+    if (boot_grid < 1 || static_cast<int64_t>(boot_grid) * STREAM_TILE_X < 16ll * k) return;
+    const int64_t want_rows = (6ll * k * n + cap - 1) / cap;
+    int64_t boot_tiles = std::max<int64_t>(boot_grid, (want_rows + STREAM_TILE_X - 1) / STREAM_TILE_X);
+    // the launch lasts as long as its busiest CTA: a few tiles past a whole wave are not worth
+    // another round (2,625,000 rows: 301 tiles -> 296 = 2 per SM; the sample shrinks by < 1/8 wave)
+    if (boot_tiles > boot_grid && boot_tiles % boot_grid < boot_grid / 8) boot_tiles -= boot_tiles % boot_grid;
+    // ... and only while reading the sample twice costs less than the two launch + refresh
+    // rounds it replaces (~45 us): option bootstrap_max_mb (16-bit bytes of the sample).
+    // At d = 768, k = 10 that is a shard of up to ~3M rows -- one GPU of eight on the 21M-row
+    // corpus; a whole-corpus GPU keeps the geometric schedule (measured: DESIGN 4.1e)
+    const int64_t sample_bytes = boot_tiles * STREAM_TILE_X * d_pad * 2;
+    if (boot_tiles * 16 > tiles_all - 1 || sample_bytes > (static_cast<int64_t>(max_mb) << 20)) return;
+    *grid = boot_grid;
+    *tiles = boot_tiles;
+}
+
 // Slab sizes of the FIXED geometric schedule of the latency regime (<= 2048 queries): the sequence
 // the launch loop of tensor_search walks through, computed up front for the one-launch streaming
 // search (stream_search.cuh).  `slab` = size of the first slab.
@@ -852,27 +880,8 @@ int tensor_search(b2ip_handle h, const float* q32, int64_t nq, int k, float* d_s
         // part of the corpus (k <= 42 at the default capacity).
         int boot_grid = 0;
         int64_t boot_tiles = 0;
-        if (use_stream && !fused_stream && h->bootstrap && !h->dbg && n > slab) {
-            // full tiles only (every group holds a row), the sample at most 1/16 of the corpus, and
-            // >= 16 groups per wanted result (two of the k best rows rarely share a group)
-            const int64_t tiles_all = (n + STREAM_TILE_X - 1) / STREAM_TILE_X;
-            boot_grid = static_cast<int>(std::min<int64_t>(std::min<int64_t>(h->sm_count, BOOT_MAX_GROUPS / STREAM_TILE_X),
-                                                           (tiles_all - 1) / 16));
-            const int64_t want_rows = (6ll * k * n + cap - 1) / cap;
-            boot_tiles = std::max<int64_t>(boot_grid, (want_rows + STREAM_TILE_X - 1) / STREAM_TILE_X);
-            // the launch lasts as long as its busiest CTA: a few tiles past a whole wave are not worth
-            // another round (2,625,000 rows: 301 tiles -> 296 = 2 per SM; the sample shrinks by < 1/8 wave)
-            if (boot_grid > 0 && boot_tiles > boot_grid && boot_tiles % boot_grid < boot_grid / 8)
-                boot_tiles -= boot_tiles % boot_grid;
-            // ... and only while reading the sample twice costs less than the two launch + refresh
-            // rounds it replaces (~45 us): option bootstrap_max_mb (16-bit bytes of the sample).
-            // At d = 768, k = 10 that is a shard of up to ~3M rows -- one GPU of eight on the 21M-row
-            // corpus; a whole-corpus GPU keeps the geometric schedule (measured: DESIGN 4.1e)
-            const int64_t sample_bytes = boot_tiles * STREAM_TILE_X * h->d_pad * 2;
-            if (static_cast<int64_t>(boot_grid) * STREAM_TILE_X < 16ll * k || boot_tiles * 16 > tiles_all - 1 ||
-                sample_bytes > (static_cast<int64_t>(h->bootstrap_max_mb) << 20))
-                boot_grid = 0;
-        }
+        if (use_stream && !fused_stream && h->bootstrap && !h->dbg && n > slab)
+            plan_bootstrap(n, k, cap, h->sm_count, h->d_pad, h->bootstrap_max_mb, &boot_grid, &boot_tiles);
         const bool bootstrap = boot_grid > 0;
         if (bootstrap) CAP_RC(ensure(h, h->gmax, static_cast<size_t>(nq_s) * boot_grid * STREAM_TILE_X * sizeof(uint32_t)));
         prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, h->stream>>>(
@@ -2004,6 +2013,13 @@ int b2ip_stats(b2ip_handle h, b2ip_stats_t* out) {
 }
 
 const char* b2ip_last_error(b2ip_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int b2ip_debug_plan_bootstrap(int64_t n_rows, int k, int cap, int sm_count, int d_pad, int max_mb,
+                              int* grid, int64_t* tiles) {
+    if (!grid || !tiles) return B2IP_ERR_INVALID;
+    plan_bootstrap(n_rows, k, cap, sm_count, d_pad, max_mb, grid, tiles);
+    return B2IP_OK;
+}
 
 int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev, int64_t row0,
                              int64_t n_rows, float* out_dev) {

@@ -264,6 +264,13 @@ const char* b2ip_last_error(b2ip_handle h);
 int b2ip_debug_coarse_scores(b2ip_handle h, int64_t nq, const float* queries_dev, int64_t row0,
                              int64_t n_rows, float* out_dev);
 
+/* Test hook, host arithmetic only (no CUDA call: usable without a GPU): the corpus sample a batch of
+ * <= 64 queries would take its first threshold from -- *grid CTAs over *tiles tiles of 128 rows --
+ * on a shard of n_rows rows for the given k, list capacity, SM count, padded dimension and
+ * "bootstrap_max_mb"; *grid = 0 when the geometric slab schedule is kept. */
+int b2ip_debug_plan_bootstrap(int64_t n_rows, int k, int cap, int sm_count, int d_pad, int max_mb,
+                              int* grid, int64_t* tiles);
+
 /* Library build info: "b2ip <version> sm_100a ..." */
 const char* b2ip_version(void);
 

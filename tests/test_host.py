@@ -41,6 +41,50 @@ def test_library_exports_every_declared_symbol(built):
     assert declared <= exported
 
 
+def test_bootstrap_sample_plan_invariants(built):
+    """Host arithmetic of the latency regime's threshold bootstrap (csrc/b2ip_api.cu::plan_bootstrap,
+    no CUDA call): swept over corpus sizes from one row to billions -- it must never fault (a zero
+    grid once divided: SIGFPE on corpora of fewer than 17 tiles) and a taken sample must satisfy what
+    the kernels rely on: every CTA sees a tile, only full tiles, >= 16 groups per wanted result, at
+    most 1/16 of the corpus, at most `bootstrap_max_mb` of 16-bit rows."""
+    import ctypes
+    lib = built.load()
+
+    def plan(n, k, cap=4096, sms=148, d_pad=768, max_mb=64):
+        grid, tiles = ctypes.c_int32(-1), ctypes.c_int64(-1)
+        assert lib.b2ip_debug_plan_bootstrap(n, k, cap, sms, d_pad, max_mb, ctypes.byref(grid), ctypes.byref(tiles)) == 0
+        return grid.value, tiles.value
+
+    rng = np.random.default_rng(0)
+    sizes = list(range(1, 4200, 7)) + [int(x) for x in 10 ** rng.uniform(3, 10.5, 4000)] + \
+        [2_625_000, 2_650_112, 21_000_000, 2 ** 31 - 1, 2 ** 32 - 1]
+    taken = 0
+    for n in sizes:
+        k = int(rng.choice([1, 2, 10, 10, 10, 33, 42, 64, 100, 1000, 2048]))
+        sms = int(rng.choice([1, 2, 16, 132, 148, 148, 160, 200]))
+        d_pad = int(rng.choice([64, 128, 768, 768, 1024, 4096]))
+        cap = max(4096, 4 * k)
+        max_mb = int(rng.choice([0, 1, 64, 64, 1 << 20]))
+        grid, tiles = plan(n, k, cap, sms, d_pad, max_mb)
+        if grid == 0:
+            assert tiles == 0
+            continue
+        taken += 1
+        full_tiles = n // 128
+        assert 1 <= grid <= min(sms, 160) and tiles >= grid
+        assert grid * 128 >= 16 * k
+        assert tiles * 16 <= (n + 127) // 128 - 1
+        stride = full_tiles // tiles                       # tile t = rows [t * stride * 128, +128)
+        assert stride >= 16 and (tiles - 1) * stride + 1 <= full_tiles
+        assert tiles * 128 * d_pad * 2 <= max_mb << 20
+        # sized for an expected list fill of cap / 6 (less a few tiles cut to a whole wave)
+        assert tiles * 128 >= (6 * k * n / cap) * (1 - 1 / 8) - 128 or tiles == grid
+    assert taken > 200
+    # the benchmark's shapes: one GPU of eight takes the sample, a whole-corpus GPU does not
+    assert plan(2_625_000, 10) == (148, 296) and plan(21_000_000, 10) == (0, 0)
+    assert plan(2_625_000, 100) == (0, 0) and plan(300, 1) == (0, 0) and plan(0, 10) == (0, 0)
+
+
 def test_library_is_sm100a_tcgen05_code(built):
     """The shipped kernels are Blackwell-native: tcgen05 MMA, TMA and TMEM loads in the SASS."""
     sass = subprocess.run(["cuobjdump", "-sass", built.LIB_PATH], capture_output=True, text=True).stdout
