@@ -32,6 +32,22 @@ def test_oracle_matches_fp64_truth(n, nq, k, d, use_blas):
     fo.compare_topk(D, I, D64.astype(np.float32), I64, q, x, rtol=1e-5)
 
 
+@pytest.mark.parametrize("n,nq,k,d", [(20000, 64, 100, 768), (6000, 12, 10, 256), (9000, 300, 1000, 128)])
+def test_oracle_matches_an_independent_fp32_blas_topk(n, nq, k, d):
+    """A second, unrelated fp32 implementation of the same contract -- torch on the CPU: its own
+    sgemm (MKL / oneDNN, not the OpenBLAS the restatement calls), the WHOLE score matrix at once
+    instead of 4096 x 1024 blocks, `torch.topk` instead of faiss's heap / reservoir handlers --
+    must give the restatement's answer up to fp32 ties.  (Not a pin to faiss itself: that needs
+    faiss; it guards the blocked handlers of the restatement against a different code path.)"""
+    torch = pytest.importorskip("torch")
+    x, q = synth(n, d, 31), synth(nq, d, 32)
+    x[7000 % n] = x[11]                                   # one exact duplicate
+    D, I = fo.search(q, x, k)
+    S = torch.from_numpy(q) @ torch.from_numpy(x).T
+    top = torch.topk(S, k, dim=1, largest=True, sorted=True)
+    fo.compare_topk(D, I, top.values.numpy(), top.indices.numpy().astype(np.int64), q, x, rtol=1e-5)
+
+
 def test_oracle_unnormalised_fp16_valued():
     x = (synth(3000, 768, 5, normalize=False) * 0.3).astype(np.float16).astype(np.float32)
     q = (synth(30, 768, 6, normalize=False) * 0.3).astype(np.float16).astype(np.float32)
