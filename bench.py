@@ -586,6 +586,25 @@ def parity_probe(torch, dist, D, res, q_dev, k, d, lo, hi, world, rank, dev, row
             "pass": bool(ok)}
 
 
+def run_guarded(fn, torch, dist, world, group):
+    """Runs one secondary workload; returns None, or what went wrong (a string) -- on EVERY rank.
+    A secondary workload must not cost the primary line, so its error is recorded instead of
+    raised.  N > 1: the searches are collective, so the ranks agree on the outcome over a host-side
+    (gloo) group first; a rank that failed ALONE finds nobody there, times out (the group's
+    timeout) and the job fails loudly instead of hanging in a half-entered NCCL collective."""
+    err = None
+    try:
+        fn()
+    except Exception as e:  # noqa: BLE001
+        err = f"{type(e).__name__}: {e}"[:400]
+    if world > 1:
+        flag = torch.tensor([1 if err else 0], dtype=torch.int32)
+        dist.all_reduce(flag, group=group)
+        if int(flag.item()) and not err:
+            err = "failed on another rank"
+    return err
+
+
 def main():
     t_start = time.perf_counter()
     args = parse()
@@ -783,20 +802,7 @@ def main():
         }
 
     def guarded(name, fn):
-        # a secondary workload must not cost the primary line: its error is recorded under its name
-        # instead of raised.  N > 1: the searches are collective, so the ranks agree on the outcome
-        # over a host-side group first (a rank that failed ALONE finds nobody there, times out and
-        # the job fails loudly instead of hanging in a half-entered NCCL collective)
-        err = None
-        try:
-            fn()
-        except Exception as e:  # noqa: BLE001
-            err = f"{type(e).__name__}: {e}"[:400]
-        if world > 1:
-            flag = torch.tensor([1 if err else 0], dtype=torch.int32)
-            dist.all_reduce(flag, group=guard_group)
-            if int(flag.item()) and not err:
-                err = "failed on another rank"
+        err = run_guarded(fn, torch, dist, world, guard_group)
         if err:
             secondary[name] = {"error": err}
 

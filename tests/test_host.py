@@ -277,6 +277,47 @@ def test_sharded_search_gloo_world2(tmp_path):
         assert p.returncode == 0 and f"rank {r} ok" in o, o[-3000:]
 
 
+_GUARD_WORKER = r'''
+import datetime, os, sys
+import torch, torch.distributed as dist
+sys.path[:0] = [ROOT]
+import bench
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["MASTER_PORT"], rank=rank, world_size=world)
+group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=60))
+ran = []
+def ok(): ran.append("ok")
+def boom(): raise RuntimeError("secondary went wrong on rank %d" % rank)
+def boom_on_1():
+    if rank == 1: raise ValueError("only here")
+assert bench.run_guarded(ok, torch, dist, world, group) is None and ran == ["ok"]
+e = bench.run_guarded(boom, torch, dist, world, group)                 # every rank fails: every rank records it
+assert e is not None and e.startswith("RuntimeError: secondary went wrong on rank %d" % rank), e
+e = bench.run_guarded(boom_on_1, torch, dist, world, group)            # one rank fails: all of them learn it
+assert (e == "failed on another rank") if rank == 0 else e.startswith("ValueError: only here"), e
+assert bench.run_guarded(ok, torch, dist, world, group) is None         # and the job goes on, in step
+assert bench.run_guarded(boom, torch, dist, 1, None).startswith("RuntimeError")   # world 1: no collective
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_bench_secondary_guard_agrees_across_ranks_gloo_world2(tmp_path):
+    """bench.run_guarded: a failing secondary workload is recorded, not fatal, and the ranks of a
+    torchrun job take the same decision (world_size 2 over gloo; bench.py is imported without a GPU)."""
+    script = tmp_path / "guard_worker.py"
+    script.write_text(f"ROOT = {ROOT!r}\n" + _GUARD_WORKER)
+    port = str(31000 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"rank {r} ok" in o, o[-3000:]
+
+
 def test_bench_reference_arm_prints_contract_line():
     """`--impl reference` under a torchrun-like environment (OMP_NUM_THREADS=1 exported): the CPU
     arm must take every host core anyway, search the FULL (here: small) corpus, and report the
