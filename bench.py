@@ -341,6 +341,10 @@ def run_reference(args):
                    f"host threads {cores} (OMP_NUM_THREADS/OPENBLAS_NUM_THREADS forced before load, whatever "
                    "torchrun exported)"),
         "queries_per_step": nq_s, "rows": rows, "seconds_per_step": t,
+        "batch_note": ("queries per step are what fits the time budget (--ref-budget-s over warm-up + timed steps); "
+                       "faiss blocks the corpus in 1,024-row sgemm calls, so a batch of ~100 queries runs the BLAS "
+                       "well below its rate for >= 512 queries per step (the main arm's cpu_baseline uses 512: "
+                       "~1.6x the queries/s of a 96-query step on the same cores)") if nq_s < 512 else None,
         "gflops": 2.0 * nq_s * rows * args.d / t / 1e9, "corpus_to_host_s": t_gen,
         "scaled_to": None if rows == args.n_corpus else {
             "n_corpus": args.n_corpus, "factor": scale,
