@@ -85,6 +85,49 @@ def test_bootstrap_sample_plan_invariants(built):
     assert plan(2_625_000, 100) == (0, 0) and plan(300, 1) == (0, 0) and plan(0, 10) == (0, 0)
 
 
+def test_bootstrap_group_maxima_bound_the_kth_score(built):
+    """The exactness argument of the threshold bootstrap, on a numpy model of the
+    kernel's indexing fed by the product's own planner: tile t of the sample = rows
+    [t * stride * 128, +128), group of a row = (t mod grid) * 128 + its slot in the tile.  The groups
+    are disjoint, so the k-th largest group maximum can never exceed the k-th best score of the
+    corpus -- for ANY scores, clustered neighbours included -- and is the sample's own k-th best
+    whenever no two of its k best rows share a group."""
+    import ctypes
+    lib = built.load()
+    rng = np.random.default_rng(5)
+    for n, k, sms in [(300_000, 10, 148), (50_000, 1, 148), (9_000, 10, 148), (1_000_000, 33, 132), (123_457, 7, 16)]:
+        grid, tiles = ctypes.c_int32(), ctypes.c_int64()
+        lib.b2ip_debug_plan_bootstrap(n, k, 4096, sms, 768, 256, ctypes.byref(grid), ctypes.byref(tiles))
+        grid, tiles = grid.value, tiles.value
+        assert grid > 0
+        stride = (n // 128) // tiles
+        t = np.arange(tiles)
+        rows = (t[:, None] * stride * 128 + np.arange(128)[None, :])             # [tiles, 128]
+        groups = ((t % grid)[:, None] * 128 + np.arange(128)[None, :])
+        assert rows.max() < n and len(np.unique(rows)) == rows.size
+        for trial in range(3):
+            scores = rng.standard_normal(n).astype(np.float32)
+            if trial == 1:        # neighbouring rows score alike: runs of 16 near-equal top scores in sampled tiles
+                for r0 in rows[rng.integers(0, tiles, 6), 0]:
+                    scores[r0:r0 + 16] = 5.0 + 1e-3 * rng.standard_normal(16)
+            if trial == 2:        # NaN scores are "empty" (ordered word 0), -inf is a real score
+                scores[rows[0, :5]] = np.nan
+                scores[rows[-1, 3]] = -np.inf
+            gmax = np.full(grid * 128, -np.inf, dtype=np.float32)
+            s_rows = np.where(np.isnan(scores[rows]), -np.inf, scores[rows])
+            np.maximum.at(gmax, groups.ravel(), s_rows.ravel())
+            bound = np.sort(gmax)[::-1][k - 1]
+            finite = np.where(np.isnan(scores), -np.inf, scores)
+            kth_corpus = np.sort(finite)[::-1][k - 1]
+            kth_sample = np.sort(s_rows.ravel())[::-1][k - 1]
+            assert bound <= kth_sample <= kth_corpus
+            top_groups = groups.ravel()[np.argsort(s_rows.ravel())[::-1][:k]]
+            if len(np.unique(top_groups)) == k:
+                assert bound == kth_sample
+            # the filtered slab admits every row of the exact top-k (threshold = bound - 2 eps <= bound)
+            assert (finite[np.argsort(finite)[::-1][:k]] >= bound).all()
+
+
 def test_library_is_sm100a_tcgen05_code(built):
     """The shipped kernels are Blackwell-native: tcgen05 MMA, TMA and TMEM loads in the SASS."""
     sass = subprocess.run(["cuobjdump", "-sass", built.LIB_PATH], capture_output=True, text=True).stdout
